@@ -1,0 +1,261 @@
+// tcgen05 attention for the Conformer block (head_dim 48, T' <= 640, key-padding mask by length).
+// Replaces F.scaled_dot_product_attention / flash_attn_varlen in
+// gigaam/encoder.py:258-277 (RotaryPositionMultiHeadAttention) on the q/k/v produced by the fused
+// LN+RoPE -> GEMM kernels.
+//
+//   qkv : [B*T, 2304] fp16 = [q(768) | k(768) | v(768)], head h at columns h*48 .. h*48+47 of each part
+//   out : [B*T, 768]  fp16
+//
+// One CTA per (q tile of 128 rows, head, utterance):
+//   warp 0    : TMA - Q tile and all K / V blocks (128 keys x 64 columns, SWIZZLE_128B; the 16 columns
+//               past the 48 real ones belong to the next head and are never multiplied: the QK^T MMA
+//               runs K = 3 x 16, and the 16 extra output columns of P.V are dropped)
+//   warp 1    : tcgen05.mma issue.  S = Q K^T (128 x 128 x 48) into TMEM, O += P V (128 x 64 x 128)
+//               with P from shared memory (K-major) and V straight from its [key, d] layout (MN-major B).
+//   warps 2-5 : softmax, one thread per query row (tcgen05.ld 32x32b), two passes over the key blocks:
+//               pass 1 = row max, pass 2 = exp2 / row sum / P -> smem.  S is recomputed in pass 2
+//               (tensor time is negligible here) so O never needs rescaling.
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace gam {
+namespace {
+
+constexpr int kAttnThreads = 192;
+constexpr int kMaxKB = 5;           // up to 640 keys
+constexpr int kTileBytes = 128 * 128;  // 128 rows x 64 fp16
+constexpr uint32_t kTmemColsAttn = 256;
+constexpr uint32_t kOCol = 128;
+
+struct AttnParams {
+  int T;
+  int nkb;
+  const int* klen;  // may be null
+  __half* out;
+  int ld_out;
+  int dk;
+  float scale_log2;
+};
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(kAttnThreads) attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
+                                                                const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sP = smem + kTileBytes;                 // 2 chunks of 64 keys
+  uint8_t* sK = sP + 2 * kTileBytes;               // nkb tiles
+  uint8_t* sV = sK + p.nkb * kTileBytes;           // nkb tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + p.nkb * kTileBytes);
+  uint64_t* kv_full = bars;            // [kMaxKB]
+  uint64_t* s_full = bars + kMaxKB;
+  uint64_t* s_empty = s_full + 1;
+  uint64_t* p_full = s_full + 2;
+  uint64_t* p_empty = s_full + 3;
+  uint64_t* o_full = s_full + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 5);
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int q0 = blockIdx.x * 128;
+  const int h = blockIdx.y;
+  const int b = blockIdx.z;
+  const int row0 = b * p.T;
+  const int nkb = p.nkb;
+
+  if (warp_idx == 0 && ptx::elect_one()) {
+    ptx::prefetch_tmap(&tmap_qkv);
+    for (int i = 0; i < kMaxKB; ++i) ptx::mbar_init(&kv_full[i], 1);
+    ptx::mbar_init(s_full, 1);
+    ptx::mbar_init(s_empty, 4);
+    ptx::mbar_init(p_full, 4);
+    ptx::mbar_init(p_empty, 1);
+    ptx::mbar_init(o_full, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp_idx == 1) ptx::tmem_alloc<kTmemColsAttn>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int dmodel = p.ld_out;  // 768
+
+  if (warp_idx == 0) {
+    if (ptx::elect_one()) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        ptx::mbar_arrive_expect_tx(&kv_full[kb], (kb == 0 ? 3 : 2) * kTileBytes);
+        if (kb == 0) ptx::tma_load_2d(sQ, &tmap_qkv, &kv_full[0], h * p.dk, row0 + q0);
+        ptx::tma_load_2d(sK + kb * kTileBytes, &tmap_qkv, &kv_full[kb], dmodel + h * p.dk, row0 + kb * 128);
+        ptx::tma_load_2d(sV + kb * kTileBytes, &tmap_qkv, &kv_full[kb], 2 * dmodel + h * p.dk, row0 + kb * 128);
+      }
+    }
+  } else if (warp_idx == 1) {
+    constexpr uint32_t kIdescS = ptx::make_idesc_f16(128, 128, 0, 0);
+    constexpr uint32_t kIdescPV = ptx::make_idesc_f16(128, 64, 0, 1);  // B (= V) is MN-major
+    const int ksteps_qk = p.dk / 16;
+    int it = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        if (it > 0) ptx::mbar_wait(s_empty, (it - 1) & 1);
+        if (pass == 0) ptx::mbar_wait(&kv_full[kb], 0);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          const uint32_t qa = ptx::smem_u32(sQ);
+          const uint32_t ka = ptx::smem_u32(sK + kb * kTileBytes);
+          for (int k = 0; k < ksteps_qk; ++k) {
+            ptx::mma_f16_ss(tmem_base, ptx::make_smem_desc_sw128(qa + k * 32, 16, 1024),
+                            ptx::make_smem_desc_sw128(ka + k * 32, 16, 1024), kIdescS, k != 0 ? 1u : 0u);
+          }
+          ptx::mma_commit(s_full);
+        }
+        __syncwarp();
+        if (pass == 1) {
+          ptx::mbar_wait(p_full, kb & 1);
+          ptx::tc_fence_after();
+          if (ptx::elect_one()) {
+            const uint32_t pa = ptx::smem_u32(sP);
+            const uint32_t va = ptx::smem_u32(sV + kb * kTileBytes);
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+              const uint64_t da = ptx::make_smem_desc_sw128(pa + (ks >> 2) * kTileBytes + (ks & 3) * 32, 16, 1024);
+              const uint64_t db = ptx::make_smem_desc_sw128(va + ks * 2048, 1024, 1024);
+              ptx::mma_f16_ss(tmem_base + kOCol, da, db, kIdescPV, (kb | ks) != 0 ? 1u : 0u);
+            }
+            ptx::mma_commit(p_empty);
+            if (kb == nkb - 1) ptx::mma_commit(o_full);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    const int quad = warp_idx & 3;
+    const int lane = threadIdx.x & 31;
+    const int r = quad * 32 + lane;
+    const uint32_t t_s = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    int klen = p.T;
+    if (p.klen != nullptr) klen = min(max(p.klen[b], 0), p.T);
+    int it = 0;
+    float m = -INFINITY;
+    // ---------------- pass 1: row max over valid keys
+    for (int kb = 0; kb < nkb; ++kb, ++it) {
+      ptx::mbar_wait(s_full, it & 1);
+      ptx::tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        const int key0 = kb * 128 + c * 32;
+        if (key0 >= klen) break;
+        uint32_t v[32];
+        ptx::tmem_ld_32x32b_x32(t_s + c * 32, v);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (key0 + j < klen) m = fmaxf(m, __uint_as_float(v[j]));
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(s_empty);
+    }
+    if (m == -INFINITY) m = 0.f;
+    const float mc = m * p.scale_log2;
+    float sum = 0.f;
+    // ---------------- pass 2: p = exp2((s - m) * scale), P -> smem (K-major, SWIZZLE_128B)
+    for (int kb = 0; kb < nkb; ++kb, ++it) {
+      ptx::mbar_wait(s_full, it & 1);
+      ptx::tc_fence_after();
+      uint32_t pk[64];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int key0 = kb * 128 + c * 32;
+        uint32_t v[32];
+        ptx::tmem_ld_32x32b_x32(t_s + c * 32, v);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          float p0 = (key0 + j < klen) ? ex2(fmaf(__uint_as_float(v[j]), p.scale_log2, -mc)) : 0.f;
+          float p1 = (key0 + j + 1 < klen) ? ex2(fmaf(__uint_as_float(v[j + 1]), p.scale_log2, -mc)) : 0.f;
+          sum += p0 + p1;
+          __half2 hh = __floats2half2_rn(p0, p1);
+          pk[c * 16 + (j >> 1)] = *reinterpret_cast<uint32_t*>(&hh);
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(s_empty);
+      ptx::mbar_wait(p_empty, (kb & 1) ^ 1);
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          uint4 val = make_uint4(pk[ch * 32 + j * 4], pk[ch * 32 + j * 4 + 1], pk[ch * 32 + j * 4 + 2], pk[ch * 32 + j * 4 + 3]);
+          *reinterpret_cast<uint4*>(sP + ch * kTileBytes + r * 128 + ((j ^ (r & 7)) << 4)) = val;
+        }
+      }
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(p_full);
+    }
+    // ---------------- epilogue: O / sum -> fp16
+    ptx::mbar_wait(o_full, 0);
+    ptx::tc_fence_after();
+    const float inv = sum > 0.f ? 1.0f / sum : 0.f;
+    const int q = q0 + r;
+    __half* dst = p.out + static_cast<size_t>(row0 + q) * p.ld_out + h * p.dk;
+    for (int c = 0; c < p.dk; c += 16) {
+      uint32_t v[16];
+      ptx::tmem_ld_32x32b_x16(t_s + kOCol + c, v);
+      ptx::tmem_ld_wait();
+      if (q < p.T) {
+        uint32_t o[8];
+#pragma unroll
+        for (int j = 0; j < 16; j += 2) {
+          __half2 hh = __floats2half2_rn(__uint_as_float(v[j]) * inv, __uint_as_float(v[j + 1]) * inv);
+          o[j >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+        }
+        uint4* d4 = reinterpret_cast<uint4*>(dst + c);
+        d4[0] = make_uint4(o[0], o[1], o[2], o[3]);
+        d4[1] = make_uint4(o[4], o[5], o[6], o[7]);
+      }
+    }
+    ptx::tc_fence_before();
+  }
+
+  __syncthreads();
+  if (warp_idx == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<kTmemColsAttn>(tmem_base);
+  }
+}
+
+}  // namespace
+
+int attention_smem_bytes(int nkb) { return (3 + 2 * nkb) * kTileBytes + 128 + 1024; }
+
+int launch_attention(const CUtensorMap* tmap_qkv, const int* klen, __half* out, int B, int T, int H, int dk, int d_model,
+                     cudaStream_t s) {
+  const int nkb = (T + 127) / 128;
+  if (nkb > kMaxKB || dk % 16 != 0 || dk > 64) return -1;
+  AttnParams p;
+  p.T = T;
+  p.nkb = nkb;
+  p.klen = klen;
+  p.out = out;
+  p.ld_out = d_model;
+  p.dk = dk;
+  p.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(dk));
+  const int smem = attention_smem_bytes(nkb);
+  static int attr_set = 0;
+  if (!attr_set) {
+    cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attention_smem_bytes(kMaxKB));
+    attr_set = 1;
+  }
+  dim3 grid((T + 127) / 128, H, B);
+  attention_kernel<<<grid, kAttnThreads, smem, s>>>(*tmap_qkv, p);
+  return 0;
+}
+
+}  // namespace gam

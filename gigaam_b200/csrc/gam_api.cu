@@ -1,0 +1,429 @@
+// C-ABI + host engine of libgigaam_b200.so: weight/plan bookkeeping, TMA descriptor construction,
+// and the kernel sequence of the path.  No compute lives here and nothing here falls back to a CPU
+// or library implementation: every stage is one of the hand-written kernels in this directory.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/gigaam_b200.h"
+#include "kernels.h"
+
+namespace gam {
+
+// ------------------------------------------------------------------ driver entry point for TMA descriptors
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+
+static int init_encode() {
+  if (g_encode) return 0;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || fn == nullptr ||
+      q != cudaDriverEntryPointSuccess)
+    return -1;
+  g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  return 0;
+}
+
+// 2-D fp16 row-major tensor [rows, cols] with row pitch ld_elems; box = [box_rows, box_cols], SWIZZLE_128B
+int make_tmap_2d_f16(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems, uint32_t box_rows,
+                     uint32_t box_cols) {
+  if (init_encode() != 0) return -1;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld_elems * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -static_cast<int>(r) - 1000;
+}
+
+// 4-D channels-last activation [B, T1, F1, C] fp16 for the stride-2 3x3 conv: box = 8 time x 16 freq x 64 ch,
+// traversal stride 2 on time and freq (so boxDim is 16 / 32 elements in tensor coordinates).
+static int make_tmap_conv4d(CUtensorMap* m, const void* base, uint64_t B, uint64_t T1, uint64_t F1, uint64_t C) {
+  if (init_encode() != 0) return -1;
+  cuuint64_t dims[4] = {C, F1, T1, B};
+  cuuint64_t strides[3] = {C * 2, F1 * C * 2, T1 * F1 * C * 2};
+  cuuint32_t box[4] = {64, 32, 16, 1};
+  cuuint32_t estr[4] = {1, 2, 2, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -static_cast<int>(r) - 1000;
+}
+
+static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+
+struct LayerMaps {
+  CUtensorMap ff1_w1, ff1_w2, w_qk, w_v, w_o, pw1, pw2, ff2_w1, ff2_w2;
+};
+
+struct Plan {
+  int B = 0;
+  int64_t M = 0;
+  void* ws = nullptr;
+  // geometry
+  int T1 = 0, F1 = 0, T2 = 0, F2 = 0, R = 0;
+  // workspace carve-up
+  int *len0 = nullptr, *len1 = nullptr, *len2 = nullptr;
+  __half *s1 = nullptr, *s2 = nullptr, *a16 = nullptr, *r16 = nullptr, *big16 = nullptr, *o16 = nullptr, *g16 = nullptr;
+  float* x = nullptr;
+  int64_t bytes = 0;
+  CUtensorMap m_s1, m_s2, m_a16, m_r16, m_hid, m_qkv, m_o16;
+};
+
+}  // namespace gam
+
+using namespace gam;
+
+struct gam_handle {
+  gam_config cfg;
+  gam_weights w;
+  std::vector<gam_layer_weights> layers;
+  std::vector<LayerMaps> lmaps;
+  CUtensorMap m_sub2_w, m_sub_out_w;
+  int device = 0;
+  int num_sms = 148;
+  int64_t launches = 0;
+  std::string err;
+  std::vector<Plan*> plans;
+};
+
+namespace {
+
+int fail(gam_handle* h, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (h) h->err = buf;
+  return code;
+}
+
+int sub_out_len(int len, int k, int pad) {
+  // floor((len + 2p - k) / 2 + 1) with float semantics of the reference (encoder.py:86-90)
+  float l = static_cast<float>(len);
+  l = floorf((l + (2 * pad - k)) / 2.0f + 1.0f);
+  return static_cast<int>(l);
+}
+
+void plan_geometry(const gam_handle* h, int B, int64_t M, Plan* p) {
+  const gam_config& c = h->cfg;
+  const int k = c.subs_kernel_size, pad = (k - 1) / 2;
+  p->B = B;
+  p->M = M;
+  p->T1 = sub_out_len(static_cast<int>(M), k, pad);
+  p->T2 = sub_out_len(p->T1, k, pad);
+  p->F1 = sub_out_len(c.feat_in, k, pad);
+  p->F2 = sub_out_len(p->F1, k, pad);
+  p->R = B * p->T2;
+}
+
+// carve the workspace; returns total bytes.  base may be null (size query).
+int64_t plan_carve(const gam_handle* h, Plan* p, uint8_t* base) {
+  const gam_config& c = h->cfg;
+  const int64_t d = c.d_model, R = p->R, B = p->B;
+  const int64_t wide = (c.d_ff > 3 * d ? c.d_ff : 3 * d);
+  int64_t off = 0;
+  auto take = [&](int64_t bytes) -> uint8_t* {
+    uint8_t* ptr = base ? base + off : nullptr;
+    off += align_up(bytes, 1024);
+    return ptr;
+  };
+  p->len0 = reinterpret_cast<int*>(take(B * 4));
+  p->len1 = reinterpret_cast<int*>(take(B * 4));
+  p->len2 = reinterpret_cast<int*>(take(B * 4));
+  p->x = reinterpret_cast<float*>(take(R * d * 4));
+  p->a16 = reinterpret_cast<__half*>(take(R * d * 2));
+  p->r16 = reinterpret_cast<__half*>(take(R * d * 2));
+  p->big16 = reinterpret_cast<__half*>(take(R * wide * 2));
+  p->o16 = reinterpret_cast<__half*>(take(R * d * 2));
+  p->g16 = reinterpret_cast<__half*>(take(R * d * 2));
+  p->s2 = reinterpret_cast<__half*>(take(R * static_cast<int64_t>(p->F2) * d * 2));
+  p->s1 = reinterpret_cast<__half*>(take(B * static_cast<int64_t>(p->T1) * p->F1 * d * 2));
+  return off;
+}
+
+int64_t decode_ws_bytes(const gam_handle* h, int B, int T) {
+  // CTC: labels [B*T] i32 ; RNNT: encproj [B*T, joint_hidden] f32
+  const int64_t R = static_cast<int64_t>(B) * T;
+  int64_t a = align_up(R * 4, 1024);
+  int64_t b = align_up(R * (h->cfg.joint_hidden > 0 ? h->cfg.joint_hidden : 1) * 4, 1024);
+  return a + b;
+}
+
+Plan* get_plan(gam_handle* h, int B, int64_t M, void* ws, int64_t ws_bytes) {
+  for (Plan* p : h->plans)
+    if (p->B == B && p->M == M && p->ws == ws) return p;
+  Plan* p = new Plan();
+  plan_geometry(h, B, M, p);
+  p->ws = ws;
+  p->bytes = plan_carve(h, p, static_cast<uint8_t*>(ws));
+  if (p->bytes > ws_bytes) {
+    fail(h, -1, "workspace too small: need %lld bytes, got %lld", (long long)p->bytes, (long long)ws_bytes);
+    delete p;
+    return nullptr;
+  }
+  const gam_config& c = h->cfg;
+  const uint64_t d = c.d_model, R = p->R;
+  int rc = 0;
+  rc |= make_tmap_conv4d(&p->m_s1, p->s1, B, p->T1, p->F1, d);
+  rc |= make_tmap_2d_f16(&p->m_s2, p->s2, R, static_cast<uint64_t>(p->F2) * d, static_cast<uint64_t>(p->F2) * d, 128, 64);
+  rc |= make_tmap_2d_f16(&p->m_a16, p->a16, R, d, d, 128, 64);
+  rc |= make_tmap_2d_f16(&p->m_r16, p->r16, R, d, d, 128, 64);
+  rc |= make_tmap_2d_f16(&p->m_hid, p->big16, R, c.d_ff, c.d_ff, 128, 64);
+  rc |= make_tmap_2d_f16(&p->m_qkv, p->big16, R, 3 * d, 3 * d, 128, 64);
+  rc |= make_tmap_2d_f16(&p->m_o16, p->o16, R, d, d, 128, 64);
+  if (rc != 0) {
+    fail(h, -2, "cuTensorMapEncodeTiled failed for activation maps (rc=%d)", rc);
+    delete p;
+    return nullptr;
+  }
+  if (h->plans.size() >= 16) {
+    delete h->plans.front();
+    h->plans.erase(h->plans.begin());
+  }
+  h->plans.push_back(p);
+  return p;
+}
+
+#define GAM_CHECK_LAUNCH(h, what)                                                             \
+  do {                                                                                        \
+    cudaError_t e__ = cudaPeekAtLastError();                                                  \
+    if (e__ != cudaSuccess) return fail(h, -3, "%s: %s", what, cudaGetErrorString(e__));      \
+  } while (0)
+
+}  // namespace
+
+extern "C" {
+
+int gam_version(void) { return 100; }
+
+const char* gam_last_error(const gam_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+int64_t gam_launch_count(const gam_handle* h) { return h ? h->launches : 0; }
+
+int gam_create(const gam_config* cfg, const gam_weights* w, int device, gam_handle** out) {
+  if (!cfg || !w || !out) return -1;
+  *out = nullptr;
+  gam_handle* h = new gam_handle();
+  h->cfg = *cfg;
+  h->w = *w;
+  h->device = device;
+  *out = h;  // returned even on failure so the caller can read gam_last_error()
+  const gam_config& c = h->cfg;
+  if (c.subsampling != 0) return fail(h, -10, "only conv2d subsampling is built in this round (got %d)", c.subsampling);
+  if (c.self_attention != 0) return fail(h, -10, "only rotary self-attention is built in this round");
+  if (c.d_model != 768 || c.d_model % c.n_heads != 0 || (c.d_model / c.n_heads) % 16 != 0)
+    return fail(h, -10, "unsupported d_model/n_heads (%d/%d): kernels are specialised for d_model 768, d_k %% 16 == 0",
+                c.d_model, c.n_heads);
+  if (c.d_ff % 256 != 0 || c.subs_kernel_size != 3) return fail(h, -10, "unsupported d_ff / subs_kernel_size");
+  if (c.win_length != c.n_fft) return fail(h, -10, "win_length != n_fft is not supported");
+  if (cudaSetDevice(device) != cudaSuccess) return fail(h, -11, "cudaSetDevice(%d) failed", device);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(h, -11, "cudaGetDeviceProperties failed");
+  if (prop.major != 10) return fail(h, -12, "sm_100a kernels need a Blackwell (cc 10.x) device, found cc %d.%d", prop.major, prop.minor);
+  h->num_sms = prop.multiProcessorCount;
+  if (init_encode() != 0) return fail(h, -13, "cuTensorMapEncodeTiled entry point not available");
+  if (gemm_init() != 0) return fail(h, -14, "cudaFuncSetAttribute failed for the GEMM kernels: %s", cudaGetErrorString(cudaGetLastError()));
+  h->layers.assign(w->layers, w->layers + c.n_layers);
+  h->w.layers = h->layers.data();
+  h->lmaps.resize(c.n_layers);
+  const uint64_t d = c.d_model, ff = c.d_ff;
+  int rc = 0;
+  for (int l = 0; l < c.n_layers; ++l) {
+    const gam_layer_weights& lw = h->layers[l];
+    LayerMaps& lm = h->lmaps[l];
+    rc |= make_tmap_2d_f16(&lm.ff1_w1, lw.ff1_w1, ff, d, d, 256, 64);
+    rc |= make_tmap_2d_f16(&lm.ff1_w2, lw.ff1_w2, d, ff, ff, 256, 64);
+    rc |= make_tmap_2d_f16(&lm.w_qk, lw.w_qk, 2 * d, d, d, 256, 64);
+    rc |= make_tmap_2d_f16(&lm.w_v, lw.w_v, d, d, d, 256, 64);
+    rc |= make_tmap_2d_f16(&lm.w_o, lw.w_o, d, d, d, 256, 64);
+    rc |= make_tmap_2d_f16(&lm.pw1, lw.pw1_w, 2 * d, d, d, 256, 64);
+    rc |= make_tmap_2d_f16(&lm.pw2, lw.pw2_w, d, d, d, 256, 64);
+    rc |= make_tmap_2d_f16(&lm.ff2_w1, lw.ff2_w1, ff, d, d, 256, 64);
+    rc |= make_tmap_2d_f16(&lm.ff2_w2, lw.ff2_w2, d, ff, ff, 256, 64);
+  }
+  const int pad = (c.subs_kernel_size - 1) / 2;
+  const int F1 = sub_out_len(c.feat_in, c.subs_kernel_size, pad), F2 = sub_out_len(F1, c.subs_kernel_size, pad);
+  if (F1 != 32 || F2 != 16) return fail(h, -10, "conv2d subsampling kernels are specialised for feat_in 64 (F1=32,F2=16)");
+  rc |= make_tmap_2d_f16(&h->m_sub2_w, w->sub2_w, d, 9 * d, 9 * d, 256, 64);
+  rc |= make_tmap_2d_f16(&h->m_sub_out_w, w->sub_out_w, d, static_cast<uint64_t>(F2) * d, static_cast<uint64_t>(F2) * d, 256, 64);
+  if (rc != 0) return fail(h, -2, "cuTensorMapEncodeTiled failed for weight maps (rc=%d)", rc);
+  return 0;
+}
+
+void gam_destroy(gam_handle* h) {
+  if (!h) return;
+  for (Plan* p : h->plans) delete p;
+  delete h;
+}
+
+int64_t gam_logmel_frames(const gam_handle* h, int64_t n) {
+  const gam_config& c = h->cfg;
+  if (c.center) return n / c.hop_length + 1;
+  return n < c.win_length ? 0 : (n - c.win_length) / c.hop_length + 1;
+}
+
+int64_t gam_encoded_frames(const gam_handle* h, int64_t M) {
+  Plan p;
+  plan_geometry(h, 1, M, &p);
+  return p.T2;
+}
+
+int64_t gam_workspace_bytes(const gam_handle* h, int32_t B, int64_t M) {
+  Plan p;
+  plan_geometry(h, B, M, &p);
+  return plan_carve(h, &p, nullptr) + decode_ws_bytes(h, B, p.T2) + 4096;
+}
+
+int gam_logmel(gam_handle* h, const float* wav, int32_t B, int64_t n_samples, float* mel, void* stream) {
+  const gam_config& c = h->cfg;
+  const int64_t M = gam_logmel_frames(h, n_samples);
+  if (M <= 0) return fail(h, -1, "waveform too short: %lld samples", (long long)n_samples);
+  if (c.center && n_samples <= c.n_fft / 2) return fail(h, -1, "reflect padding needs more than n_fft/2 samples");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (launch_logmel(wav, B, static_cast<int>(n_samples), static_cast<int>(M), h->w.window, h->w.dft_cos, h->w.dft_sin,
+                    h->w.mel_fb, mel, c.n_fft, c.hop_length, c.center, c.n_mels, s) != 0)
+    return fail(h, -1, "logmel: unsupported n_fft/n_mels (%d/%d)", c.n_fft, c.n_mels);
+  h->launches += 1;
+  GAM_CHECK_LAUNCH(h, "logmel");
+  return 0;
+}
+
+int gam_encode(gam_handle* h, const float* mel, const int64_t* mel_len, int32_t B, int64_t M, void* workspace,
+               int64_t workspace_bytes, float* enc, int32_t* enc_len, int32_t n_layers_run, void* stream) {
+  const gam_config& c = h->cfg;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Plan* p = get_plan(h, B, M, workspace, workspace_bytes);
+  if (!p) return -1;
+  if (p->T2 <= 0) return fail(h, -1, "input too short for the subsampling (M=%lld)", (long long)M);
+  if ((p->T2 + 127) / 128 > 5) return fail(h, -1, "T'=%d exceeds the attention kernel's 640-frame limit", p->T2);
+  const int d = c.d_model, R = p->R, nsm = h->num_sms;
+  const int L = (n_layers_run < 0 || n_layers_run > c.n_layers) ? c.n_layers : n_layers_run;
+  int rc = 0;
+
+  launch_sub_lengths(reinterpret_cast<const long long*>(mel_len), B, 2 * ((c.subs_kernel_size - 1) / 2) - c.subs_kernel_size,
+                     static_cast<int>(M), p->len0, p->len1, p->len2, s);
+  rc |= launch_subsample_conv1(mel, p->len0, p->len1, h->w.sub1_w, h->w.sub1_b, p->s1, B, static_cast<int>(M), c.feat_in,
+                               p->T1, p->F1, d, s);
+  rc |= launch_gemm_conv(&p->m_s1, &h->m_sub2_w, B, p->T2, d, d, h->w.sub2_b, p->len2, p->s2, d, nsm, s);
+  h->launches += 3;
+  GAM_CHECK_LAUNCH(h, "subsampling");
+  if (rc) return fail(h, -4, "subsampling launch rejected (rc=%d)", rc);
+
+  float* xdst = (L == 0) ? enc : p->x;  // n_layers_run == 0 -> return pre_encode output
+  rc |= launch_gemm(GEMM_BIAS_F32, &p->m_s2, &h->m_sub_out_w, R, d, p->F2 * d, h->w.sub_out_b, nullptr, xdst, d, 1.f, nsm, s);
+  h->launches += 1;
+  if (L > 0) {
+    launch_ln_f16(p->x, h->layers[0].ln_ff1_g, h->layers[0].ln_ff1_b, p->a16, R, s);
+    h->launches += 1;
+  }
+  const int dk = d / c.n_heads;
+  for (int l = 0; l < L; ++l) {
+    const gam_layer_weights& w = h->layers[l];
+    const LayerMaps& m = h->lmaps[l];
+    // x += 0.5 * FF1(LN(x))                                     (encoder.py:480-483)
+    rc |= launch_gemm(GEMM_BIAS_SILU_F16, &p->m_a16, &m.ff1_w1, R, c.d_ff, d, w.ff1_b1, nullptr, p->big16, c.d_ff, 1.f, nsm, s);
+    rc |= launch_gemm(GEMM_BIAS_RES_F32, &p->m_hid, &m.ff1_w2, R, d, c.d_ff, w.ff1_b2, p->x, p->x, d, 0.5f, nsm, s);
+    // x += W_o attn(q = W_q rope(u), k = W_k rope(u), v = W_v u), u = LN(x)   (encoder.py:485-487, 236-277)
+    launch_ln_rope_f16(p->x, w.ln_att_g, w.ln_att_b, h->w.rope_cos, h->w.rope_sin, p->a16, p->r16, R, p->T2, dk / 2, s);
+    rc |= launch_gemm(GEMM_BIAS_F16, &p->m_r16, &m.w_qk, R, 2 * d, d, w.b_qk, nullptr, p->big16, 3 * d, 1.f, nsm, s);
+    rc |= launch_gemm(GEMM_BIAS_F16, &p->m_a16, &m.w_v, R, d, d, w.b_v, nullptr, p->big16 + 2 * d, 3 * d, 1.f, nsm, s);
+    rc |= launch_attention(&p->m_qkv, B > 1 ? p->len2 : nullptr, p->o16, B, p->T2, c.n_heads, dk, d, s);
+    rc |= launch_gemm(GEMM_BIAS_RES_F32, &p->m_o16, &m.w_o, R, d, d, w.b_o, p->x, p->x, d, 1.f, nsm, s);
+    // x += Conv(LN(x))                                           (encoder.py:489-491, 396-409)
+    launch_ln_f16(p->x, w.ln_conv_g, w.ln_conv_b, p->a16, R, s);
+    rc |= launch_gemm(GEMM_BIAS_GLU_F16, &p->m_a16, &m.pw1, R, 2 * d, d, w.pw1_b, nullptr, p->g16, d, 1.f, nsm, s);
+    if (c.conv_norm == 0)
+      rc |= launch_dwconv_bn_silu(p->g16, w.dw_w, w.dw_b, p->len2, p->o16, B, p->T2, c.conv_kernel_size, s);
+    else
+      rc |= launch_dwconv_ln_silu(p->g16, w.dw_w, w.dw_b, w.cn_g, w.cn_b, p->len2, p->o16, B, p->T2, c.conv_kernel_size, s);
+    rc |= launch_gemm(GEMM_BIAS_RES_F32, &p->m_o16, &m.pw2, R, d, d, w.pw2_b, p->x, p->x, d, 1.f, nsm, s);
+    // x += 0.5 * FF2(LN(x))                                      (encoder.py:493-495)
+    launch_ln_f16(p->x, w.ln_ff2_g, w.ln_ff2_b, p->a16, R, s);
+    rc |= launch_gemm(GEMM_BIAS_SILU_F16, &p->m_a16, &m.ff2_w1, R, c.d_ff, d, w.ff2_b1, nullptr, p->big16, c.d_ff, 1.f, nsm, s);
+    rc |= launch_gemm(GEMM_BIAS_RES_F32, &p->m_hid, &m.ff2_w2, R, d, c.d_ff, w.ff2_b2, p->x, p->x, d, 0.5f, nsm, s);
+    // x = LN_out(x) (+ next layer's first LN fused)                (encoder.py:497)
+    if (l + 1 < L)
+      launch_ln_out_ln(p->x, w.ln_out_g, w.ln_out_b, h->layers[l + 1].ln_ff1_g, h->layers[l + 1].ln_ff1_b, p->x, p->a16, R, s);
+    else
+      launch_ln_out_ln(p->x, w.ln_out_g, w.ln_out_b, nullptr, nullptr, enc, nullptr, R, s);
+    h->launches += 15;
+    if (rc) return fail(h, -4, "layer %d: a launch was rejected (rc=%d)", l, rc);
+  }
+  cudaMemcpyAsync(enc_len, p->len2, B * sizeof(int), cudaMemcpyDeviceToDevice, s);
+  GAM_CHECK_LAUNCH(h, "encode");
+  return 0;
+}
+
+int gam_ctc_greedy(gam_handle* h, const float* enc, const int32_t* enc_len, int32_t B, int32_t T, void* workspace,
+                   int64_t workspace_bytes, int32_t* ids, int32_t* frames, int32_t* counts, int32_t max_out, void* stream) {
+  const gam_config& c = h->cfg;
+  if (c.head != 1) return fail(h, -1, "model has no CTC head");
+  if (max_out < T) return fail(h, -1, "max_out (%d) must be >= T (%d)", max_out, T);
+  if (max_out != T) return fail(h, -1, "ids/frames row pitch must equal T for the CTC path");
+  const int64_t R = static_cast<int64_t>(B) * T;
+  if (workspace_bytes < R * 4) return fail(h, -1, "workspace too small for CTC labels");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int* labels = static_cast<int*>(workspace);
+  launch_ctc_argmax(enc, h->w.ctc_w, h->w.ctc_b, labels, static_cast<int>(R), c.d_model, c.num_classes, s);
+  launch_ctc_collapse(labels, enc_len, B, T, c.num_classes - 1, ids, frames, counts, s);
+  h->launches += 2;
+  GAM_CHECK_LAUNCH(h, "ctc_greedy");
+  return 0;
+}
+
+int gam_rnnt_greedy(gam_handle* h, const float* enc, const int32_t* enc_len, int32_t B, int32_t T, void* workspace,
+                    int64_t workspace_bytes, int32_t* ids, int32_t* frames, int32_t* counts, int32_t max_out, void* stream) {
+  const gam_config& c = h->cfg;
+  if (c.head != 2) return fail(h, -1, "model has no RNN-T head");
+  if (c.pred_hidden != c.joint_hidden) return fail(h, -1, "pred_hidden != joint_hidden is not supported");
+  const int64_t R = static_cast<int64_t>(B) * T;
+  if (workspace_bytes < R * c.joint_hidden * 4) return fail(h, -1, "workspace too small for the RNN-T encoder projection");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  float* encproj = static_cast<float*>(workspace);
+  launch_sgemm_tn_bias(enc, h->w.rnnt_enc_w, h->w.rnnt_enc_b, encproj, static_cast<int>(R), c.joint_hidden, c.d_model, s);
+  if (launch_rnnt_greedy(encproj, enc_len, h->w.rnnt_emb_gates, h->w.rnnt_whh_t, h->w.rnnt_wp_t, h->w.rnnt_bp, h->w.rnnt_wo,
+                         h->w.rnnt_bo, B, T, c.pred_hidden, c.num_classes, c.num_classes - 1, c.max_symbols, max_out, ids,
+                         frames, counts, s) != 0)
+    return fail(h, -1, "rnnt: hidden size %d exceeds the kernel limit", c.pred_hidden);
+  h->launches += 2;
+  GAM_CHECK_LAUNCH(h, "rnnt_greedy");
+  return 0;
+}
+
+int gam_test_gemm(gam_handle* h, int32_t kind, const void* A, const void* W, const float* bias, const float* res, void* out,
+                  int32_t M, int32_t N, int32_t K, int32_t ldo, float scale, void* stream) {
+  CUtensorMap ta, tw;
+  int rc = make_tmap_2d_f16(&ta, A, M, K, K, 128, 64);
+  rc |= make_tmap_2d_f16(&tw, W, N, K, K, 256, 64);
+  if (rc) return fail(h, -2, "tensor map encode failed (rc=%d)", rc);
+  rc = launch_gemm(kind, &ta, &tw, M, N, K, bias, res, out, ldo, scale, h->num_sms, static_cast<cudaStream_t>(stream));
+  h->launches += 1;
+  if (rc) return fail(h, -4, "gemm launch rejected (rc=%d)", rc);
+  GAM_CHECK_LAUNCH(h, "test_gemm");
+  return 0;
+}
+
+int gam_test_attention(gam_handle* h, const void* qkv, const int32_t* klen, void* out, int32_t B, int32_t T, void* stream) {
+  const gam_config& c = h->cfg;
+  CUtensorMap tq;
+  const uint64_t d = c.d_model;
+  int rc = make_tmap_2d_f16(&tq, qkv, static_cast<uint64_t>(B) * T, 3 * d, 3 * d, 128, 64);
+  if (rc) return fail(h, -2, "tensor map encode failed (rc=%d)", rc);
+  rc = launch_attention(&tq, klen, static_cast<__half*>(out), B, T, c.n_heads, c.d_model / c.n_heads, c.d_model,
+                        static_cast<cudaStream_t>(stream));
+  h->launches += 1;
+  if (rc) return fail(h, -4, "attention launch rejected (T=%d)", T);
+  GAM_CHECK_LAUNCH(h, "test_attention");
+  return 0;
+}
+
+}  // extern "C"

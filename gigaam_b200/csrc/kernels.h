@@ -1,0 +1,68 @@
+// Internal launcher declarations shared by the translation units of libgigaam_b200.so.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gam {
+
+// rowops.cu
+void launch_ln_f16(const float* x, const float* g, const float* b, __half* out, int rows, cudaStream_t s);
+void launch_ln_rope_f16(const float* x, const float* g, const float* b, const float* rope_cos, const float* rope_sin,
+                        __half* out_u, __half* out_r, int rows, int T, int half_dim, cudaStream_t s);
+void launch_ln_out_ln(const float* r, const float* g_out, const float* b_out, const float* g_next, const float* b_next,
+                      float* x_out, __half* y_out, int rows, cudaStream_t s);
+int launch_dwconv_bn_silu(const __half* g, const float* w, const float* bias, const int* len, __half* out, int B, int T,
+                          int kw, cudaStream_t s);
+int launch_dwconv_ln_silu(const __half* g, const float* w, const float* bias, const float* gamma, const float* beta,
+                          const int* len, __half* out, int B, int T, int kw, cudaStream_t s);
+void launch_sub_lengths(const long long* mel_len, int B, int pad2_minus_k, int max_T0, int* len0, int* len1, int* len2,
+                        cudaStream_t s);
+
+// frontend.cu
+int launch_logmel(const float* wav, int B, int n_samples, int n_frames, const float* window, const float* tcos,
+                  const float* tsin, const float* fb, float* mel, int n_fft, int hop, int center, int n_mels,
+                  cudaStream_t s);
+int launch_subsample_conv1(const float* mel, const int* len0, const int* len1, const float* w, const float* bias,
+                           __half* out, int B, int M, int F, int T1, int F1, int C, cudaStream_t s);
+
+// attention_sm100.cu
+int launch_attention(const CUtensorMap* tmap_qkv, const int* klen, __half* out, int B, int T, int H, int dk, int d_model,
+                     cudaStream_t s);
+
+// ctc.cu
+void launch_ctc_argmax(const float* enc, const float* W, const float* bias, int* labels, int R, int D, int V1,
+                       cudaStream_t s);
+void launch_ctc_collapse(const int* labels, const int* len, int B, int T, int blank, int* ids, int* frames, int* counts,
+                         cudaStream_t s);
+
+// rnnt.cu
+void launch_sgemm_tn_bias(const float* A, const float* W, const float* bias, float* C, int M, int N, int K, cudaStream_t s);
+int launch_rnnt_greedy(const float* encproj, const int* len, const float* emb_gates, const float* whhT, const float* wpT,
+                       const float* bp, const float* wo, const float* bo, int B, int T, int H, int V1, int blank,
+                       int max_symbols, int max_out, int* ids, int* frames, int* counts, cudaStream_t s);
+
+// gemm.cu
+struct GemmParams;
+enum GemmKind : int {
+  GEMM_BIAS_F16 = 0,
+  GEMM_BIAS_SILU_F16 = 1,
+  GEMM_BIAS_GLU_F16 = 2,
+  GEMM_BIAS_RES_F32 = 3,
+  GEMM_BIAS_F32 = 4,
+  GEMM_CONV_RELU_MASK_F16 = 5,
+};
+// 2-D operand GEMM  D[M,N] = A[M,K] W[N,K]^T with fused epilogue `kind`; N % 256 == 0, K % 64 == 0.
+int launch_gemm(int kind, const CUtensorMap* tmap_a, const CUtensorMap* tmap_w, int M, int N, int K, const float* bias,
+                const float* res, void* out, int ldo, float scale, int num_sms, cudaStream_t s);
+// implicit-GEMM 3x3/s2 conv over channels-last [B,T1,F1,C] (tmap_a 4-D strided), output [B*T2*16, N] fp16
+int launch_gemm_conv(const CUtensorMap* tmap_a4d, const CUtensorMap* tmap_w, int B, int T2, int C, int N, const float* bias,
+                     const int* len2, void* out, int ldo, int num_sms, cudaStream_t s);
+int gemm_init();
+
+// tensor maps (gam_api.cu)
+int make_tmap_2d_f16(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems, uint32_t box_rows,
+                     uint32_t box_cols);
+
+}  // namespace gam

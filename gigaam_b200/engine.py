@@ -1,0 +1,272 @@
+"""Host side of the C ABI: packs a reference state_dict into the device layout the kernels want, owns the
+gam_handle and the scratch workspace, and turns torch tensors into raw pointers.  No arithmetic of the path is
+done here -- only one-off weight re-layout at load time (BatchNorm folding, q/k concatenation, GLU row pairing,
+conv weight permutation, fp16 casts, DFT / rotary tables)."""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import _lib
+
+Tensor = torch.Tensor
+
+
+def _cfg_get(section, key, default=None):
+    if isinstance(section, dict):
+        return section.get(key, default)
+    return getattr(section, key, default) if hasattr(section, key) else (section.get(key, default) if hasattr(section, "get") else default)
+
+
+class Engine:
+    """One model replica on one CUDA device."""
+
+    def __init__(self, cfg: Dict, state_dict: Dict[str, Tensor], device: torch.device):
+        if device.type != "cuda":
+            raise RuntimeError("gigaam_b200 runs on CUDA (sm_100a) devices only; there is no CPU path")
+        self.lib = _lib.load()
+        self.device = device
+        self.cfg = cfg
+        self._keep: List[Tensor] = []
+        self._ws: Dict[Tuple[int, int], Tensor] = {}
+        self.handle = C.c_void_p()
+        pre, enc = cfg["preprocessor"], cfg["encoder"]
+        head = cfg.get("head") if isinstance(cfg, dict) else None
+        sr = _cfg_get(pre, "sample_rate")
+        self.n_fft = _cfg_get(pre, "n_fft", sr // 40)
+        self.win = _cfg_get(pre, "win_length", sr // 40)
+        self.hop = _cfg_get(pre, "hop_length", sr // 100)
+        self.center = bool(_cfg_get(pre, "center", True))
+        self.n_mels = _cfg_get(pre, "features")
+        self.d_model = enc["d_model"]
+        self.n_layers = enc["n_layers"]
+        self.n_heads = enc["n_heads"]
+        self.d_ff = self.d_model * enc["ff_expansion_factor"]
+        if enc["self_attention_model"] != "rotary":
+            raise NotImplementedError("rel_pos self-attention (v1_* checkpoints) is not built yet")
+        if enc["subsampling"] != "conv2d":
+            raise NotImplementedError("conv1d subsampling (v3_* checkpoints) is not built yet")
+        self.head_type = 0
+        self.num_classes = 0
+        self.max_symbols = 10
+        gc = _lib.GamConfig()
+        gc.sample_rate, gc.n_mels, gc.n_fft, gc.win_length, gc.hop_length, gc.center = sr, self.n_mels, self.n_fft, self.win, self.hop, int(self.center)
+        gc.feat_in, gc.n_layers, gc.d_model, gc.n_heads, gc.d_ff = enc["feat_in"], self.n_layers, self.d_model, self.n_heads, self.d_ff
+        gc.subsampling = 0 if enc["subsampling"] == "conv2d" else 1
+        gc.subs_kernel_size = enc["subs_kernel_size"]
+        gc.conv_kernel_size = enc["conv_kernel_size"]
+        gc.conv_norm = 0 if enc["conv_norm_type"] == "batch_norm" else 1
+        gc.self_attention = 0
+        gc.pos_emb_max_len = enc["pos_emb_max_len"]
+        gw = _lib.GamWeights()
+        sd = state_dict
+        self._pack_frontend(gw, sd)
+        self._pack_subsampling(gw, sd, enc)
+        self._pack_rope(gw, enc)
+        self._layers = (_lib.GamLayerWeights * self.n_layers)()
+        for l in range(self.n_layers):
+            self._pack_layer(self._layers[l], sd, l, enc)
+        gw.layers = C.cast(self._layers, C.POINTER(_lib.GamLayerWeights))
+        if head is not None:
+            if head["type"] == "ctc":
+                self.head_type, self.num_classes = 1, head["num_classes"]
+                gw.ctc_w = self._dev(sd["head.decoder_layers.0.weight"].reshape(self.num_classes, -1).float())
+                gw.ctc_b = self._dev(sd["head.decoder_layers.0.bias"].float())
+            else:
+                self._pack_rnnt(gw, gc, sd, head)
+                self.max_symbols = int(_cfg_get(cfg.get("decoding", {}), "max_symbols_per_step", 10))
+        gc.head, gc.num_classes, gc.max_symbols = self.head_type, self.num_classes, self.max_symbols
+        with torch.cuda.device(device):
+            rc = self.lib.gam_create(C.byref(gc), C.byref(gw), device.index or 0, C.byref(self.handle))
+        _lib.check(self.lib, self.handle, rc, "gam_create")
+
+    # ------------------------------------------------------------------ packing helpers
+    def _dev(self, t: Tensor, dtype: Optional[torch.dtype] = None) -> int:
+        t = t.detach()
+        if dtype is not None:
+            t = t.to(dtype)
+        t = t.to(self.device).contiguous()
+        self._keep.append(t)
+        return t.data_ptr()
+
+    def _pack_frontend(self, gw, sd):
+        n = self.n_fft
+        K = n // 2 + 1
+        window = sd["preprocessor.featurizer.0.spectrogram.window"].float()
+        if window.numel() != n:
+            raise NotImplementedError("win_length != n_fft")
+        idx = torch.arange(K, dtype=torch.float64)
+        ang = 2.0 * math.pi * torch.outer(idx, idx) / n  # [n, k]
+        gw.window = self._dev(window)
+        gw.dft_cos = self._dev(torch.cos(ang).float())
+        gw.dft_sin = self._dev(torch.sin(ang).float())
+        gw.mel_fb = self._dev(sd["preprocessor.featurizer.0.mel_scale.fb"].float())
+
+    def _pack_subsampling(self, gw, sd, enc):
+        p = "encoder.pre_encode."
+        d = self.d_model
+        w1 = sd[p + "conv.0.weight"].float()                     # [C, 1, 3, 3]
+        gw.sub1_w = self._dev(w1.reshape(d, 9))
+        gw.sub1_b = self._dev(sd[p + "conv.0.bias"].float())
+        w2 = sd[p + "conv.2.weight"].float()                     # [C_out, C_in, kt, kf]
+        gw.sub2_w = self._dev(w2.permute(0, 2, 3, 1).reshape(d, 9 * d), torch.float16)
+        gw.sub2_b = self._dev(sd[p + "conv.2.bias"].float())
+        wo = sd[p + "out.weight"].float()                        # [d, C*F2] with K index c*F2 + f
+        f2 = wo.shape[1] // d
+        gw.sub_out_w = self._dev(wo.reshape(d, d, f2).permute(0, 2, 1).reshape(d, f2 * d), torch.float16)
+        gw.sub_out_b = self._dev(sd[p + "out.bias"].float())
+
+    def _pack_rope(self, gw, enc):
+        dk = self.d_model // self.n_heads
+        base = enc["pos_emb_max_len"]  # the reference passes pos_emb_max_len as the rotary base (encoder.py:546-548)
+        inv_freq = 1.0 / (base ** (torch.arange(0, dk, 2).float() / dk))
+        t = torch.arange(enc["pos_emb_max_len"]).float()
+        freqs = torch.einsum("i,j->ij", t, inv_freq)             # [max_len, dk/2]
+        gw.rope_cos = self._dev(freqs.cos())
+        gw.rope_sin = self._dev(freqs.sin())
+
+    def _pack_layer(self, lw, sd, l: int, enc):
+        q = f"encoder.layers.{l}."
+        d = self.d_model
+        h16 = torch.float16
+
+        def f(name):
+            return sd[q + name].float()
+
+        lw.ln_ff1_g, lw.ln_ff1_b = self._dev(f("norm_feed_forward1.weight")), self._dev(f("norm_feed_forward1.bias"))
+        lw.ff1_w1, lw.ff1_b1 = self._dev(f("feed_forward1.linear1.weight"), h16), self._dev(f("feed_forward1.linear1.bias"))
+        lw.ff1_w2, lw.ff1_b2 = self._dev(f("feed_forward1.linear2.weight"), h16), self._dev(f("feed_forward1.linear2.bias"))
+        lw.ln_att_g, lw.ln_att_b = self._dev(f("norm_self_att.weight")), self._dev(f("norm_self_att.bias"))
+        lw.w_qk = self._dev(torch.cat([f("self_attn.linear_q.weight"), f("self_attn.linear_k.weight")], 0), h16)
+        lw.b_qk = self._dev(torch.cat([f("self_attn.linear_q.bias"), f("self_attn.linear_k.bias")], 0))
+        lw.w_v, lw.b_v = self._dev(f("self_attn.linear_v.weight"), h16), self._dev(f("self_attn.linear_v.bias"))
+        lw.w_o, lw.b_o = self._dev(f("self_attn.linear_out.weight"), h16), self._dev(f("self_attn.linear_out.bias"))
+        lw.ln_conv_g, lw.ln_conv_b = self._dev(f("norm_conv.weight")), self._dev(f("norm_conv.bias"))
+        # GLU pairing: accumulator tile j (256 columns) = [value rows j*128.. | gate rows d + j*128..]
+        half = 128
+        perm = torch.cat([torch.cat([torch.arange(j * half, (j + 1) * half), d + torch.arange(j * half, (j + 1) * half)])
+                          for j in range(d // half)])
+        w1 = f("conv.pointwise_conv1.weight").reshape(2 * d, d)
+        lw.pw1_w, lw.pw1_b = self._dev(w1[perm], h16), self._dev(f("conv.pointwise_conv1.bias")[perm])
+        dw = f("conv.depthwise_conv.weight").reshape(d, -1)
+        db = f("conv.depthwise_conv.bias")
+        if enc["conv_norm_type"] == "batch_norm":
+            s = f("conv.batch_norm.weight") / torch.sqrt(f("conv.batch_norm.running_var") + 1e-5)
+            dw = dw * s[:, None]
+            db = (db - f("conv.batch_norm.running_mean")) * s + f("conv.batch_norm.bias")
+            lw.cn_g, lw.cn_b = None, None
+        else:
+            lw.cn_g, lw.cn_b = self._dev(f("conv.batch_norm.weight")), self._dev(f("conv.batch_norm.bias"))
+        lw.dw_w, lw.dw_b = self._dev(dw), self._dev(db)
+        lw.pw2_w = self._dev(f("conv.pointwise_conv2.weight").reshape(d, d), h16)
+        lw.pw2_b = self._dev(f("conv.pointwise_conv2.bias"))
+        lw.ln_ff2_g, lw.ln_ff2_b = self._dev(f("norm_feed_forward2.weight")), self._dev(f("norm_feed_forward2.bias"))
+        lw.ff2_w1, lw.ff2_b1 = self._dev(f("feed_forward2.linear1.weight"), h16), self._dev(f("feed_forward2.linear1.bias"))
+        lw.ff2_w2, lw.ff2_b2 = self._dev(f("feed_forward2.linear2.weight"), h16), self._dev(f("feed_forward2.linear2.bias"))
+        lw.ln_out_g, lw.ln_out_b = self._dev(f("norm_out.weight")), self._dev(f("norm_out.bias"))
+
+    def _pack_rnnt(self, gw, gc, sd, head):
+        dc, jt = head["decoder"], head["joint"]
+        if dc["pred_rnn_layers"] != 1:
+            raise NotImplementedError("multi-layer prediction LSTM")
+        self.head_type, self.num_classes = 2, jt["num_classes"]
+        gc.pred_hidden, gc.joint_hidden = dc["pred_hidden"], jt["joint_hidden"]
+        emb = sd["head.decoder.embed.weight"].double()
+        w_ih, w_hh = sd["head.decoder.lstm.weight_ih_l0"].double(), sd["head.decoder.lstm.weight_hh_l0"].float()
+        bias = sd["head.decoder.lstm.bias_ih_l0"].double() + sd["head.decoder.lstm.bias_hh_l0"].double()
+        gw.rnnt_emb_gates = self._dev((emb @ w_ih.t() + bias).float())
+        gw.rnnt_whh_t = self._dev(w_hh.t())
+        gw.rnnt_wp_t = self._dev(sd["head.joint.pred.weight"].float().t())
+        gw.rnnt_bp = self._dev(sd["head.joint.pred.bias"].float())
+        gw.rnnt_enc_w = self._dev(sd["head.joint.enc.weight"].float())
+        gw.rnnt_enc_b = self._dev(sd["head.joint.enc.bias"].float())
+        gw.rnnt_wo = self._dev(sd["head.joint.joint_net.1.weight"].float())
+        gw.rnnt_bo = self._dev(sd["head.joint.joint_net.1.bias"].float())
+
+    # ------------------------------------------------------------------ calls
+    def _stream(self) -> C.c_void_p:
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def logmel_frames(self, n: int) -> int:
+        return int(self.lib.gam_logmel_frames(self.handle, int(n)))
+
+    def encoded_frames(self, m: int) -> int:
+        return int(self.lib.gam_encoded_frames(self.handle, int(m)))
+
+    def workspace(self, B: int, M: int) -> Tensor:
+        key = (B, M)
+        ws = self._ws.get(key)
+        if ws is None:
+            nbytes = int(self.lib.gam_workspace_bytes(self.handle, B, M))
+            if len(self._ws) >= 4:
+                self._ws.pop(next(iter(self._ws)))
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self._ws[key] = ws
+        return ws
+
+    def logmel(self, wav: Tensor) -> Tensor:
+        """[B, N] f32 on device -> [B, n_mels, M] f32 (FeatureExtractor.forward, gigaam/preprocess.py:94-98)"""
+        assert wav.is_cuda and wav.dtype == torch.float32 and wav.dim() == 2
+        wav = wav.contiguous()
+        B, N = wav.shape
+        M = self.logmel_frames(N)
+        mel = torch.empty((B, self.n_mels, M), dtype=torch.float32, device=self.device)
+        rc = self.lib.gam_logmel(self.handle, wav.data_ptr(), B, N, mel.data_ptr(), self._stream())
+        _lib.check(self.lib, self.handle, rc, "gam_logmel")
+        return mel
+
+    def encode(self, mel: Tensor, mel_len: Tensor, n_layers_run: int = -1) -> Tuple[Tensor, Tensor]:
+        """[B, F, M] f32, [B] i64 -> ([B, T', d] f32 row-major, [B] i32)"""
+        assert mel.is_cuda and mel.dtype == torch.float32 and mel.dim() == 3
+        mel = mel.contiguous()
+        mel_len = mel_len.to(device=self.device, dtype=torch.int64).contiguous()
+        B, _, M = mel.shape
+        T = self.encoded_frames(M)
+        ws = self.workspace(B, M)
+        enc = torch.empty((B, T, self.d_model), dtype=torch.float32, device=self.device)
+        enc_len = torch.empty((B,), dtype=torch.int32, device=self.device)
+        rc = self.lib.gam_encode(self.handle, mel.data_ptr(), mel_len.data_ptr(), B, M, ws.data_ptr(), ws.numel(),
+                                 enc.data_ptr(), enc_len.data_ptr(), n_layers_run, self._stream())
+        _lib.check(self.lib, self.handle, rc, "gam_encode")
+        return enc, enc_len
+
+    def _decode_ws(self, B: int, T: int) -> Tensor:
+        need = B * T * 4 * max(1, 320) + 4096
+        key = (-B, T)
+        ws = self._ws.get(key)
+        if ws is None or ws.numel() < need:
+            ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+            self._ws[key] = ws
+        return ws
+
+    def greedy(self, enc_btd: Tensor, enc_len: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+        """enc [B, T, d] f32 contiguous, len [B] -> (ids [B, max_out] i32, frames, counts [B] i32) on device."""
+        assert enc_btd.is_cuda and enc_btd.dtype == torch.float32 and enc_btd.is_contiguous()
+        B, T, _ = enc_btd.shape
+        enc_len = enc_len.to(device=self.device, dtype=torch.int32).contiguous()
+        max_out = T if self.head_type == 1 else T * self.max_symbols
+        ids = torch.empty((B, max_out), dtype=torch.int32, device=self.device)
+        frames = torch.empty((B, max_out), dtype=torch.int32, device=self.device)
+        counts = torch.empty((B,), dtype=torch.int32, device=self.device)
+        ws = self._decode_ws(B, T)
+        fn = self.lib.gam_ctc_greedy if self.head_type == 1 else self.lib.gam_rnnt_greedy
+        if self.head_type == 0:
+            raise RuntimeError("model has no head to decode with")
+        rc = fn(self.handle, enc_btd.data_ptr(), enc_len.data_ptr(), B, T, ws.data_ptr(), ws.numel(), ids.data_ptr(),
+                frames.data_ptr(), counts.data_ptr(), max_out, self._stream())
+        _lib.check(self.lib, self.handle, rc, "gam_greedy")
+        return ids, frames, counts
+
+    def launch_count(self) -> int:
+        return int(self.lib.gam_launch_count(self.handle))
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None) and self.handle.value:
+                self.lib.gam_destroy(self.handle)
+                self.handle = C.c_void_p()
+        except Exception:
+            pass
