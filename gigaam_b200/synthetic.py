@@ -97,7 +97,11 @@ _GAIN = {"head.joint.joint_net.1.weight": 6.0, "head.joint.enc.weight": 3.0, "he
 
 def _param_list(cfg: Dict) -> List[Tuple[str, Tuple[int, ...], str, float]]:
     """(key, shape, kind, fan_in) in a fixed order.  kind: w|b|ln_w|ln_b|bn_mean|bn_var|int|emb"""
-    enc = cfg["encoder"]
+    return encoder_param_list(cfg["encoder"]) + head_param_list(cfg.get("head"))
+
+
+def encoder_param_list(enc: Dict) -> List[Tuple[str, Tuple[int, ...], str, float]]:
+    """state_dict entries of gigaam.encoder.ConformerEncoder (keys carry the "encoder." prefix)."""
     d, L = enc["d_model"], enc["n_layers"]
     ff = d * enc["ff_expansion_factor"]
     k = enc["subs_kernel_size"]
@@ -153,7 +157,17 @@ def _param_list(cfg: Dict) -> List[Tuple[str, Tuple[int, ...], str, float]]:
         lin(q + "feed_forward2.linear1", ff, d)
         lin(q + "feed_forward2.linear2", d, ff)
         ln(q + "norm_out")
-    head = cfg.get("head")
+    return out
+
+
+def head_param_list(head) -> List[Tuple[str, Tuple[int, ...], str, float]]:
+    """state_dict entries of gigaam.decoder.CTCHead / RNNTHead (keys carry the "head." prefix)."""
+    out: List[Tuple[str, Tuple[int, ...], str, float]] = []
+
+    def lin(prefix: str, o: int, i: int):
+        out.append((prefix + ".weight", (o, i), "w", i))
+        out.append((prefix + ".bias", (o,), "b", i))
+
     if head and head["type"] == "ctc":
         out.append(("head.decoder_layers.0.weight", (head["num_classes"], head["feat_in"], 1), "w", head["feat_in"]))
         out.append(("head.decoder_layers.0.bias", (head["num_classes"],), "b", head["feat_in"]))
