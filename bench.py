@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""Throughput of the GigaAM hot path (log-mel -> Conformer encoder -> CTC greedy) on B200.
+
+    python bench.py --gpus 1 --steps 20 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference --steps 2 --warmup 1       # the reference's CPU path (oracle port) on host cores
+
+Workload (BASELINE.json configs[1]): v2_ctc, batch 64 x 10 s synthetic 16 kHz audio per GPU (weak scaling:
+every rank runs its own 64 utterances, hypotheses all-gathered to every rank over NCCL when N > 1), seeded
+random weights of the reference's shape (no checkpoints offline).
+
+One JSON line on stdout (rank 0): see the task contract.  `value` = device-resident throughput (CUDA graph of
+the whole step, rotating input buffers larger than L2), `e2e` = the same metric through the public API
+(`model.forward` + `model.decoding.decode`) from pinned HOST buffers with the H2D / D2H copies inside the timed
+region, `roofline` = the dominant kernel class timed live with CUDA events, `cpu_baseline` = the oracle port of the
+reference's CPU path on the box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+MODEL = "v2_ctc"
+BATCH = 64
+SECONDS = 10.0
+N_ROT = 4  # rotating input buffers: 4 x 41 MB = 164 MB > 126 MB L2
+
+
+def flops_per_utterance(n_samples: int) -> dict:
+    """Algorithmic FLOPs (2 x MAC, dense, padding-free) of one utterance -- SURVEY 8(d) formulae."""
+    M = n_samples // 160 + 1
+    T1 = (M - 1) // 2 + 1
+    T = (T1 - 1) // 2 + 1
+    d, ff, L, V1 = 768, 3072, 16, 34
+    sub = 2 * 9 * d * T1 * 32 + 2 * 6912 * d * T * 16 + 2 * 12288 * d * T
+    per_frame = 2 * (2 * d * ff) * 2 + 4 * 2 * d * d + 2 * d * 2 * d + 2 * d * d + 2 * 31 * d + 4 * d * T
+    return {"T": T, "M": M, "subsampling": sub, "layers": L * per_frame * T, "head": 2 * d * V1 * T,
+            "total": sub + L * per_frame * T + 2 * d * V1 * T,
+            "gemm_ffn_up": 2 * d * ff * T, "gemm_ffn_down": 2 * d * ff * T}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference(steps: int, warmup: int, batch: int = 4, seconds: float = SECONDS):
+    """The reference's CPU PyTorch path restated (oracle/gigaam_oracle.py: same ATen ops, fp32, no autocast --
+    gigaam/model.py:34-35) on all host cores: log-mel + encoder + CTC greedy incl. host detokenisation."""
+    import torch
+    from gigaam_b200 import synthetic
+    from oracle import gigaam_oracle as orc
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    ck = synthetic.synthetic_checkpoint(MODEL, seed=0)
+    cfg, sd = ck["cfg"], ck["state_dict"]
+    wav, wav_len = synthetic.synthetic_audio(batch, seconds, seed=1234)
+    vocab = cfg["decoding"]["vocabulary"]
+
+    def step():
+        with torch.inference_mode():
+            enc, enc_len = orc.model_forward(wav, wav_len, sd, cfg)
+            hyp = orc.ctc_greedy(enc, enc_len, sd)
+        return ["".join(vocab[i] for i in ids) for ids, _ in hyp]
+
+    for _ in range(warmup):
+        step()
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+    sec = statistics.median(times)
+    return {"value": batch / sec, "unit": "utt/s", "cores": cores, "kind": "port",
+            "sample": f"{batch} x {seconds:g} s utterances of the same workload per step, median of {steps} steps after "
+                      f"{warmup} warm-up, torch {torch.__version__} fp32, {cores} threads",
+            "rtfx": batch * seconds / sec, "sec_per_step": sec}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    n_samples = int(SECONDS * 16000)
+    config = {"workload": f"{MODEL} batch={args.batch}x{SECONDS:g}s per GPU: log-mel + 16-layer Conformer encoder + CTC greedy "
+                          "(BASELINE.json configs[1])",
+              "global_batch": args.batch * max(world, 1), "audio_seconds": SECONDS, "parallelism": f"dp{max(world, 1)} (utterance sharding)",
+              "l2": f"{N_ROT} rotating input buffers ({N_ROT * args.batch * n_samples * 4 / 1e6:.0f} MB > 126 MB L2); >2 GB of "
+                    "intermediates + 465 MB weights per step"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        steps = max(1, min(args.steps, 5))
+        res = cpu_reference(steps, max(1, min(args.warmup, 1)))
+        line = {"impl": "reference", "metric": "utterances/sec (10 s audio, v2_ctc)", "value": res["value"], "unit": "utt/s",
+                "n_gpus": args.gpus, "steps": steps, "warmup": 1, "ms_per_step": res["sec_per_step"] * 1e3, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "rtfx": res["rtfx"],
+                "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": res["value"], "unit": "utt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    import gigaam_b200 as gigaam
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    model = gigaam.load_model(MODEL, device=dev, synthetic=True)  # reference defaults: fp16_encoder=True
+    eng = model._get_engine()
+    B = args.batch
+    wavs, lens = [], None
+    for i in range(N_ROT):
+        w, l = gigaam.synthetic_audio(B, SECONDS, seed=1234 + 17 * i + 1000 * rank)
+        wavs.append(w.to(dev))
+        lens = l
+    wav_len = lens.to(dev)
+    M = eng.logmel_frames(n_samples)
+    T = eng.encoded_frames(M)
+    mel_len = model.preprocessor.out_len(wav_len)
+    static_in = torch.empty_like(wavs[0])
+    gathered = [torch.empty((world * B, T), dtype=torch.int32, device=dev), torch.empty((world * B,), dtype=torch.int32, device=dev)] if world > 1 else None
+
+    def device_step(wav):
+        mel = eng.logmel(wav)
+        enc, enc_len = eng.encode(mel, mel_len)
+        ids, frames, counts = eng.greedy(enc, enc_len)
+        return ids, frames, counts
+
+    def gather(ids, counts):
+        if world > 1:  # the path's only exchange: hypotheses to every rank over NVLink
+            dist.all_gather_into_tensor(gathered[0], ids)
+            dist.all_gather_into_tensor(gathered[1], counts)
+
+    # ---- warm-up eagerly, then capture the whole step in one CUDA graph (kills ~250 launch gaps)
+    side = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            out = device_step(static_in)
+        side.synchronize()
+        launches0 = eng.launch_count()
+        out = device_step(static_in)
+        launches_per_step = eng.launch_count() - launches0
+    side.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        g_ids, g_frames, g_counts = device_step(static_in)
+
+    def graph_step(i):
+        static_in.copy_(wavs[i % N_ROT], non_blocking=True)  # device->device refill of the static input (41 MB)
+        graph.replay()
+        gather(g_ids, g_counts)
+
+    for i in range(max(args.warmup, 3)):
+        graph_step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        graph_step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    value = world * B * args.steps / (ms_total / 1e3)
+
+    # ---- end to end through the public API from pinned host memory
+    host_wavs = [w.cpu().pin_memory() for w in wavs]
+    host_len = lens.clone().pin_memory()
+
+    def api_step(i):
+        wav = host_wavs[i % N_ROT].to(dev, non_blocking=True)
+        ln = host_len.to(dev, non_blocking=True)
+        enc, enc_len = model(wav, ln)                                   # GigaAM.forward
+        hyps = model.decoding.decode(model.head, enc, enc_len)          # D2H of ids / frames / counts + detokenise
+        return hyps
+
+    for i in range(3):
+        api_step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        hyps = api_step(i)
+    torch.cuda.synchronize()
+    e2e_sec = time.perf_counter() - t0
+    t = torch.tensor([e2e_sec], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / float(t.item())
+    h2d = B * n_samples * 4 + B * 8
+    d2h = 2 * B * T * 4 + B * 4
+
+    # ---- dominant kernel, timed live with CUDA events on the launching stream
+    roofline = None
+    if rank == 0:
+        peaks = {}
+        pk = ROOT / "MEASURED_PEAKS.json"
+        if pk.exists():
+            peaks = json.loads(pk.read_text())
+        peak_tf = peaks.get("bf16_tflops_sustained") or 1400.0
+        peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)"
+        eng.profile_begin()
+        nprof = 3
+        for i in range(nprof):
+            device_step(wavs[i % N_ROT])
+        prof = eng.profile_end()
+        fl = flops_per_utterance(n_samples)
+        R = B * fl["T"]
+        cls_flops = {"gemm_ffn_up_silu": 2 * R * 768 * 3072, "gemm_ffn_down_res": 2 * R * 768 * 3072,
+                     "gemm_conv2_implicit": 2 * B * fl["T"] * 16 * 6912 * 768, "gemm_subsample_out": 2 * R * 12288 * 768,
+                     "gemm_qkv": None, "gemm_proj_res": 2 * R * 768 * 768, "gemm_pw1_glu": 2 * R * 768 * 1536}
+        total_ms = sum(v[0] for v in prof.values())
+        dom = max(prof.items(), key=lambda kv: kv[1][0])
+        name, (ms_sum, n) = dom
+        avg_ms = ms_sum / n
+        fpl = cls_flops.get(name)
+        achieved = fpl / (avg_ms * 1e-3) / 1e12 if fpl else None
+        roofline = {"kernel": name, "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                    "frac": (achieved / peak_tf) if achieved else None, "traffic": None, "peak_source": peak_src,
+                    "avg_launch_ms": avg_ms, "launches_per_step": n // nprof, "share_of_step": ms_sum / total_ms,
+                    "flops_per_launch": fpl,
+                    "step_tflops": B * fl["total"] / (ms_per_step * 1e-3) / 1e12,
+                    "step_frac": B * fl["total"] / (ms_per_step * 1e-3) / 1e12 / peak_tf,
+                    "classes_ms_per_step": {k: round(v[0] / nprof, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}}
+
+    if rank == 0:
+        cpu = None if args.no_cpu_baseline else cpu_reference(steps=2, warmup=1)
+        line = {"metric": "utterances/sec (10 s audio, v2_ctc)", "value": value, "unit": "utt/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f16 tensor-core operands, f32 accumulate/residual/norm/head",
+                "data": "synthetic", "config": config, "rtfx": value * SECONDS, "rtf": 1.0 / (value * SECONDS),
+                "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": "utt/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "api": "model(wav, len) + model.decoding.decode(model.head, enc, enc_len), pinned host wav in, python hypotheses out"},
+                "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
+                "roofline": roofline,
+                "cpu_baseline": ({k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")} if cpu else None)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

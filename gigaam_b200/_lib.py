@@ -46,7 +46,8 @@ class GamWeights(C.Structure):
 
 EXPORTS = ("gam_create", "gam_destroy", "gam_last_error", "gam_version", "gam_logmel_frames", "gam_encoded_frames",
            "gam_workspace_bytes", "gam_logmel", "gam_encode", "gam_ctc_greedy", "gam_rnnt_greedy", "gam_test_gemm",
-           "gam_test_attention", "gam_launch_count")
+           "gam_test_attention", "gam_launch_count", "gam_profile_begin", "gam_profile_end", "gam_profile_class_count",
+           "gam_profile_class_name")
 
 
 def lib_path() -> Path:
@@ -91,6 +92,13 @@ def load() -> C.CDLL:
     lib.gam_test_gemm.restype = C.c_int
     lib.gam_test_attention.argtypes = [H, c_vp, c_vp, c_vp, i32, i32, c_vp]
     lib.gam_test_attention.restype = C.c_int
+    lib.gam_profile_begin.argtypes = [H]
+    lib.gam_profile_begin.restype = C.c_int
+    lib.gam_profile_end.argtypes = [H, C.POINTER(C.c_double), C.POINTER(C.c_int64), i32]
+    lib.gam_profile_end.restype = C.c_int
+    lib.gam_profile_class_count.restype = C.c_int
+    lib.gam_profile_class_name.argtypes = [i32]
+    lib.gam_profile_class_name.restype = C.c_char_p
     _LIB = lib
     return lib
 

@@ -92,7 +92,38 @@ struct gam_handle {
   int64_t launches = 0;
   std::string err;
   std::vector<Plan*> plans;
+  // optional per-launch CUDA-event timing (bench.py's roofline leg); never active during graph capture
+  bool prof = false;
+  std::vector<cudaEvent_t> prof_ev;   // start/stop pairs
+  std::vector<int> prof_cls;
 };
+
+// kernel classes reported by gam_profile_end
+enum ProfClass : int {
+  PC_LOGMEL = 0, PC_SUB_CONV1, PC_GEMM_CONV2, PC_GEMM_SUBOUT, PC_GEMM_FFN_UP, PC_GEMM_FFN_DOWN, PC_GEMM_QKV, PC_GEMM_PROJ,
+  PC_GEMM_GLU, PC_LAYERNORM, PC_ATTENTION, PC_DWCONV, PC_CTC_ARGMAX, PC_CTC_COLLAPSE, PC_RNNT_ENCPROJ, PC_RNNT_GREEDY,
+  PC_MISC, PC_COUNT
+};
+
+struct ProfScope {
+  gam_handle* h;
+  cudaStream_t s;
+  ProfScope(gam_handle* h_, int cls, cudaStream_t s_) : h(h_), s(s_) {
+    h->launches += 1;
+    if (!h->prof) return;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    h->prof_ev.push_back(a);
+    h->prof_ev.push_back(b);
+    h->prof_cls.push_back(cls);
+    cudaEventRecord(a, s);
+  }
+  ~ProfScope() {
+    if (h->prof) cudaEventRecord(h->prof_ev.back(), s);
+  }
+};
+#define PROF(cls) ProfScope prof_scope__(h, cls, s)
 
 namespace {
 
@@ -289,10 +320,12 @@ int gam_logmel(gam_handle* h, const float* wav, int32_t B, int64_t n_samples, fl
   if (M <= 0) return fail(h, -1, "waveform too short: %lld samples", (long long)n_samples);
   if (c.center && n_samples <= c.n_fft / 2) return fail(h, -1, "reflect padding needs more than n_fft/2 samples");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (launch_logmel(wav, B, static_cast<int>(n_samples), static_cast<int>(M), h->w.window, h->w.dft_cos, h->w.dft_sin,
-                    h->w.mel_fb, mel, c.n_fft, c.hop_length, c.center, c.n_mels, s) != 0)
-    return fail(h, -1, "logmel: unsupported n_fft/n_mels (%d/%d)", c.n_fft, c.n_mels);
-  h->launches += 1;
+  {
+    PROF(PC_LOGMEL);
+    if (launch_logmel(wav, B, static_cast<int>(n_samples), static_cast<int>(M), h->w.window, h->w.dft_cos, h->w.dft_sin,
+                      h->w.mel_fb, mel, c.n_fft, c.hop_length, c.center, c.n_mels, s) != 0)
+      return fail(h, -1, "logmel: unsupported n_fft/n_mels (%d/%d)", c.n_fft, c.n_mels);
+  }
   GAM_CHECK_LAUNCH(h, "logmel");
   return 0;
 }
@@ -309,53 +342,77 @@ int gam_encode(gam_handle* h, const float* mel, const int64_t* mel_len, int32_t 
   const int L = (n_layers_run < 0 || n_layers_run > c.n_layers) ? c.n_layers : n_layers_run;
   int rc = 0;
 
-  launch_sub_lengths(reinterpret_cast<const long long*>(mel_len), B, 2 * ((c.subs_kernel_size - 1) / 2) - c.subs_kernel_size,
-                     static_cast<int>(M), p->len0, p->len1, p->len2, s);
-  rc |= launch_subsample_conv1(mel, p->len0, p->len1, h->w.sub1_w, h->w.sub1_b, p->s1, B, static_cast<int>(M), c.feat_in,
-                               p->T1, p->F1, d, s);
-  rc |= launch_gemm_conv(&p->m_s1, &h->m_sub2_w, B, p->T2, d, d, h->w.sub2_b, p->len2, p->s2, d, nsm, s);
-  h->launches += 3;
+  {
+    PROF(PC_MISC);
+    launch_sub_lengths(reinterpret_cast<const long long*>(mel_len), B, 2 * ((c.subs_kernel_size - 1) / 2) - c.subs_kernel_size,
+                       static_cast<int>(M), p->len0, p->len1, p->len2, s);
+  }
+  {
+    PROF(PC_SUB_CONV1);
+    rc |= launch_subsample_conv1(mel, p->len0, p->len1, h->w.sub1_w, h->w.sub1_b, p->s1, B, static_cast<int>(M), c.feat_in,
+                                 p->T1, p->F1, d, s);
+  }
+  {
+    PROF(PC_GEMM_CONV2);
+    rc |= launch_gemm_conv(&p->m_s1, &h->m_sub2_w, B, p->T2, d, d, h->w.sub2_b, p->len2, p->s2, d, nsm, s);
+  }
   GAM_CHECK_LAUNCH(h, "subsampling");
   if (rc) return fail(h, -4, "subsampling launch rejected (rc=%d)", rc);
 
   float* xdst = (L == 0) ? enc : p->x;  // n_layers_run == 0 -> return pre_encode output
-  rc |= launch_gemm(GEMM_BIAS_F32, &p->m_s2, &h->m_sub_out_w, R, d, p->F2 * d, h->w.sub_out_b, nullptr, xdst, d, 1.f, nsm, s);
-  h->launches += 1;
+  {
+    PROF(PC_GEMM_SUBOUT);
+    rc |= launch_gemm(GEMM_BIAS_F32, &p->m_s2, &h->m_sub_out_w, R, d, p->F2 * d, h->w.sub_out_b, nullptr, xdst, d, 1.f, nsm, s);
+  }
   if (L > 0) {
+    PROF(PC_LAYERNORM);
     launch_ln_f16(p->x, h->layers[0].ln_ff1_g, h->layers[0].ln_ff1_b, p->a16, R, s);
-    h->launches += 1;
   }
   const int dk = d / c.n_heads;
   for (int l = 0; l < L; ++l) {
     const gam_layer_weights& w = h->layers[l];
     const LayerMaps& m = h->lmaps[l];
     // x += 0.5 * FF1(LN(x))                                     (encoder.py:480-483)
-    rc |= launch_gemm(GEMM_BIAS_SILU_F16, &p->m_a16, &m.ff1_w1, R, c.d_ff, d, w.ff1_b1, nullptr, p->big16, c.d_ff, 1.f, nsm, s);
-    rc |= launch_gemm(GEMM_BIAS_RES_F32, &p->m_hid, &m.ff1_w2, R, d, c.d_ff, w.ff1_b2, p->x, p->x, d, 0.5f, nsm, s);
+    { PROF(PC_GEMM_FFN_UP);
+      rc |= launch_gemm(GEMM_BIAS_SILU_F16, &p->m_a16, &m.ff1_w1, R, c.d_ff, d, w.ff1_b1, nullptr, p->big16, c.d_ff, 1.f, nsm, s); }
+    { PROF(PC_GEMM_FFN_DOWN);
+      rc |= launch_gemm(GEMM_BIAS_RES_F32, &p->m_hid, &m.ff1_w2, R, d, c.d_ff, w.ff1_b2, p->x, p->x, d, 0.5f, nsm, s); }
     // x += W_o attn(q = W_q rope(u), k = W_k rope(u), v = W_v u), u = LN(x)   (encoder.py:485-487, 236-277)
-    launch_ln_rope_f16(p->x, w.ln_att_g, w.ln_att_b, h->w.rope_cos, h->w.rope_sin, p->a16, p->r16, R, p->T2, dk / 2, s);
-    rc |= launch_gemm(GEMM_BIAS_F16, &p->m_r16, &m.w_qk, R, 2 * d, d, w.b_qk, nullptr, p->big16, 3 * d, 1.f, nsm, s);
-    rc |= launch_gemm(GEMM_BIAS_F16, &p->m_a16, &m.w_v, R, d, d, w.b_v, nullptr, p->big16 + 2 * d, 3 * d, 1.f, nsm, s);
-    rc |= launch_attention(&p->m_qkv, B > 1 ? p->len2 : nullptr, p->o16, B, p->T2, c.n_heads, dk, d, s);
-    rc |= launch_gemm(GEMM_BIAS_RES_F32, &p->m_o16, &m.w_o, R, d, d, w.b_o, p->x, p->x, d, 1.f, nsm, s);
+    { PROF(PC_LAYERNORM);
+      launch_ln_rope_f16(p->x, w.ln_att_g, w.ln_att_b, h->w.rope_cos, h->w.rope_sin, p->a16, p->r16, R, p->T2, dk / 2, s); }
+    { PROF(PC_GEMM_QKV);
+      rc |= launch_gemm(GEMM_BIAS_F16, &p->m_r16, &m.w_qk, R, 2 * d, d, w.b_qk, nullptr, p->big16, 3 * d, 1.f, nsm, s); }
+    { PROF(PC_GEMM_QKV);
+      rc |= launch_gemm(GEMM_BIAS_F16, &p->m_a16, &m.w_v, R, d, d, w.b_v, nullptr, p->big16 + 2 * d, 3 * d, 1.f, nsm, s); }
+    { PROF(PC_ATTENTION);
+      rc |= launch_attention(&p->m_qkv, B > 1 ? p->len2 : nullptr, p->o16, B, p->T2, c.n_heads, dk, d, s); }
+    { PROF(PC_GEMM_PROJ);
+      rc |= launch_gemm(GEMM_BIAS_RES_F32, &p->m_o16, &m.w_o, R, d, d, w.b_o, p->x, p->x, d, 1.f, nsm, s); }
     // x += Conv(LN(x))                                           (encoder.py:489-491, 396-409)
-    launch_ln_f16(p->x, w.ln_conv_g, w.ln_conv_b, p->a16, R, s);
-    rc |= launch_gemm(GEMM_BIAS_GLU_F16, &p->m_a16, &m.pw1, R, 2 * d, d, w.pw1_b, nullptr, p->g16, d, 1.f, nsm, s);
-    if (c.conv_norm == 0)
-      rc |= launch_dwconv_bn_silu(p->g16, w.dw_w, w.dw_b, p->len2, p->o16, B, p->T2, c.conv_kernel_size, s);
-    else
-      rc |= launch_dwconv_ln_silu(p->g16, w.dw_w, w.dw_b, w.cn_g, w.cn_b, p->len2, p->o16, B, p->T2, c.conv_kernel_size, s);
-    rc |= launch_gemm(GEMM_BIAS_RES_F32, &p->m_o16, &m.pw2, R, d, d, w.pw2_b, p->x, p->x, d, 1.f, nsm, s);
+    { PROF(PC_LAYERNORM);
+      launch_ln_f16(p->x, w.ln_conv_g, w.ln_conv_b, p->a16, R, s); }
+    { PROF(PC_GEMM_GLU);
+      rc |= launch_gemm(GEMM_BIAS_GLU_F16, &p->m_a16, &m.pw1, R, 2 * d, d, w.pw1_b, nullptr, p->g16, d, 1.f, nsm, s); }
+    { PROF(PC_DWCONV);
+      if (c.conv_norm == 0)
+        rc |= launch_dwconv_bn_silu(p->g16, w.dw_w, w.dw_b, p->len2, p->o16, B, p->T2, c.conv_kernel_size, s);
+      else
+        rc |= launch_dwconv_ln_silu(p->g16, w.dw_w, w.dw_b, w.cn_g, w.cn_b, p->len2, p->o16, B, p->T2, c.conv_kernel_size, s); }
+    { PROF(PC_GEMM_PROJ);
+      rc |= launch_gemm(GEMM_BIAS_RES_F32, &p->m_o16, &m.pw2, R, d, d, w.pw2_b, p->x, p->x, d, 1.f, nsm, s); }
     // x += 0.5 * FF2(LN(x))                                      (encoder.py:493-495)
-    launch_ln_f16(p->x, w.ln_ff2_g, w.ln_ff2_b, p->a16, R, s);
-    rc |= launch_gemm(GEMM_BIAS_SILU_F16, &p->m_a16, &m.ff2_w1, R, c.d_ff, d, w.ff2_b1, nullptr, p->big16, c.d_ff, 1.f, nsm, s);
-    rc |= launch_gemm(GEMM_BIAS_RES_F32, &p->m_hid, &m.ff2_w2, R, d, c.d_ff, w.ff2_b2, p->x, p->x, d, 0.5f, nsm, s);
+    { PROF(PC_LAYERNORM);
+      launch_ln_f16(p->x, w.ln_ff2_g, w.ln_ff2_b, p->a16, R, s); }
+    { PROF(PC_GEMM_FFN_UP);
+      rc |= launch_gemm(GEMM_BIAS_SILU_F16, &p->m_a16, &m.ff2_w1, R, c.d_ff, d, w.ff2_b1, nullptr, p->big16, c.d_ff, 1.f, nsm, s); }
+    { PROF(PC_GEMM_FFN_DOWN);
+      rc |= launch_gemm(GEMM_BIAS_RES_F32, &p->m_hid, &m.ff2_w2, R, d, c.d_ff, w.ff2_b2, p->x, p->x, d, 0.5f, nsm, s); }
     // x = LN_out(x) (+ next layer's first LN fused)                (encoder.py:497)
-    if (l + 1 < L)
-      launch_ln_out_ln(p->x, w.ln_out_g, w.ln_out_b, h->layers[l + 1].ln_ff1_g, h->layers[l + 1].ln_ff1_b, p->x, p->a16, R, s);
-    else
-      launch_ln_out_ln(p->x, w.ln_out_g, w.ln_out_b, nullptr, nullptr, enc, nullptr, R, s);
-    h->launches += 15;
+    { PROF(PC_LAYERNORM);
+      if (l + 1 < L)
+        launch_ln_out_ln(p->x, w.ln_out_g, w.ln_out_b, h->layers[l + 1].ln_ff1_g, h->layers[l + 1].ln_ff1_b, p->x, p->a16, R, s);
+      else
+        launch_ln_out_ln(p->x, w.ln_out_g, w.ln_out_b, nullptr, nullptr, enc, nullptr, R, s); }
     if (rc) return fail(h, -4, "layer %d: a launch was rejected (rc=%d)", l, rc);
   }
   cudaMemcpyAsync(enc_len, p->len2, B * sizeof(int), cudaMemcpyDeviceToDevice, s);
@@ -373,9 +430,10 @@ int gam_ctc_greedy(gam_handle* h, const float* enc, const int32_t* enc_len, int3
   if (workspace_bytes < R * 4) return fail(h, -1, "workspace too small for CTC labels");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   int* labels = static_cast<int*>(workspace);
-  launch_ctc_argmax(enc, h->w.ctc_w, h->w.ctc_b, labels, static_cast<int>(R), c.d_model, c.num_classes, s);
-  launch_ctc_collapse(labels, enc_len, B, T, c.num_classes - 1, ids, frames, counts, s);
-  h->launches += 2;
+  { PROF(PC_CTC_ARGMAX);
+    launch_ctc_argmax(enc, h->w.ctc_w, h->w.ctc_b, labels, static_cast<int>(R), c.d_model, c.num_classes, s); }
+  { PROF(PC_CTC_COLLAPSE);
+    launch_ctc_collapse(labels, enc_len, B, T, c.num_classes - 1, ids, frames, counts, s); }
   GAM_CHECK_LAUNCH(h, "ctc_greedy");
   return 0;
 }
@@ -389,14 +447,50 @@ int gam_rnnt_greedy(gam_handle* h, const float* enc, const int32_t* enc_len, int
   if (workspace_bytes < R * c.joint_hidden * 4) return fail(h, -1, "workspace too small for the RNN-T encoder projection");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   float* encproj = static_cast<float*>(workspace);
-  launch_sgemm_tn_bias(enc, h->w.rnnt_enc_w, h->w.rnnt_enc_b, encproj, static_cast<int>(R), c.joint_hidden, c.d_model, s);
+  { PROF(PC_RNNT_ENCPROJ);
+    launch_sgemm_tn_bias(enc, h->w.rnnt_enc_w, h->w.rnnt_enc_b, encproj, static_cast<int>(R), c.joint_hidden, c.d_model, s); }
+  PROF(PC_RNNT_GREEDY);
   if (launch_rnnt_greedy(encproj, enc_len, h->w.rnnt_emb_gates, h->w.rnnt_whh_t, h->w.rnnt_wp_t, h->w.rnnt_bp, h->w.rnnt_wo,
                          h->w.rnnt_bo, B, T, c.pred_hidden, c.num_classes, c.num_classes - 1, c.max_symbols, max_out, ids,
                          frames, counts, s) != 0)
     return fail(h, -1, "rnnt: hidden size %d exceeds the kernel limit", c.pred_hidden);
-  h->launches += 2;
   GAM_CHECK_LAUNCH(h, "rnnt_greedy");
   return 0;
+}
+
+int gam_profile_begin(gam_handle* h) {
+  for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
+  h->prof_ev.clear();
+  h->prof_cls.clear();
+  h->prof = true;
+  return 0;
+}
+
+int gam_profile_end(gam_handle* h, double* ms_per_class, int64_t* launches_per_class, int32_t n_classes) {
+  h->prof = false;
+  for (int i = 0; i < n_classes; ++i) { ms_per_class[i] = 0.0; launches_per_class[i] = 0; }
+  int rc = 0;
+  for (size_t i = 0; i < h->prof_cls.size(); ++i) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(h->prof_ev[2 * i + 1]) != cudaSuccess ||
+        cudaEventElapsedTime(&ms, h->prof_ev[2 * i], h->prof_ev[2 * i + 1]) != cudaSuccess) { rc = -1; continue; }
+    const int cls = h->prof_cls[i];
+    if (cls < n_classes) { ms_per_class[cls] += ms; launches_per_class[cls] += 1; }
+  }
+  for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
+  h->prof_ev.clear();
+  h->prof_cls.clear();
+  if (rc) return fail(h, -5, "profile: an event could not be read: %s", cudaGetErrorString(cudaGetLastError()));
+  return 0;
+}
+
+int gam_profile_class_count(void) { return PC_COUNT; }
+
+const char* gam_profile_class_name(int32_t cls) {
+  static const char* names[PC_COUNT] = {"logmel", "subsample_conv1", "gemm_conv2_implicit", "gemm_subsample_out", "gemm_ffn_up_silu",
+                                        "gemm_ffn_down_res", "gemm_qkv", "gemm_proj_res", "gemm_pw1_glu", "layernorm", "attention",
+                                        "dwconv_bn_silu", "ctc_head_argmax", "ctc_collapse", "rnnt_enc_proj", "rnnt_greedy", "misc"};
+  return (cls >= 0 && cls < PC_COUNT) ? names[cls] : "?";
 }
 
 int gam_test_gemm(gam_handle* h, int32_t kind, const void* A, const void* W, const float* bias, const float* res, void* out,
@@ -405,8 +499,11 @@ int gam_test_gemm(gam_handle* h, int32_t kind, const void* A, const void* W, con
   int rc = make_tmap_2d_f16(&ta, A, M, K, K, 128, 64);
   rc |= make_tmap_2d_f16(&tw, W, N, K, K, 256, 64);
   if (rc) return fail(h, -2, "tensor map encode failed (rc=%d)", rc);
-  rc = launch_gemm(kind, &ta, &tw, M, N, K, bias, res, out, ldo, scale, h->num_sms, static_cast<cudaStream_t>(stream));
-  h->launches += 1;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  {
+    PROF(PC_MISC);
+    rc = launch_gemm(kind, &ta, &tw, M, N, K, bias, res, out, ldo, scale, h->num_sms, s);
+  }
   if (rc) return fail(h, -4, "gemm launch rejected (rc=%d)", rc);
   GAM_CHECK_LAUNCH(h, "test_gemm");
   return 0;
@@ -418,9 +515,11 @@ int gam_test_attention(gam_handle* h, const void* qkv, const int32_t* klen, void
   const uint64_t d = c.d_model;
   int rc = make_tmap_2d_f16(&tq, qkv, static_cast<uint64_t>(B) * T, 3 * d, 3 * d, 128, 64);
   if (rc) return fail(h, -2, "tensor map encode failed (rc=%d)", rc);
-  rc = launch_attention(&tq, klen, static_cast<__half*>(out), B, T, c.n_heads, c.d_model / c.n_heads, c.d_model,
-                        static_cast<cudaStream_t>(stream));
-  h->launches += 1;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  {
+    PROF(PC_ATTENTION);
+    rc = launch_attention(&tq, klen, static_cast<__half*>(out), B, T, c.n_heads, c.d_model / c.n_heads, c.d_model, s);
+  }
   if (rc) return fail(h, -4, "attention launch rejected (T=%d)", T);
   GAM_CHECK_LAUNCH(h, "test_attention");
   return 0;

@@ -21,6 +21,39 @@ def _cfg_get(section, key, default=None):
     return getattr(section, key, default) if hasattr(section, key) else (section.get(key, default) if hasattr(section, "get") else default)
 
 
+# ---------------------------------------------------------------------------------- pure weight re-layout (CPU-testable)
+def glu_row_permutation(d: int, half: int = 128) -> Tensor:
+    """Row order of pointwise_conv1 so that accumulator tile j (2*half columns) = [value rows j*half.. | gate rows d+j*half..]:
+    the GEMM epilogue then computes value * sigmoid(gate) thread-locally (gigaam/encoder.py:398-399 GLU over channels)."""
+    return torch.cat([torch.cat([torch.arange(j * half, (j + 1) * half), d + torch.arange(j * half, (j + 1) * half)])
+                      for j in range(d // half)])
+
+
+def fold_batchnorm(dw_w: Tensor, dw_b: Tensor, gamma: Tensor, beta: Tensor, mean: Tensor, var: Tensor, eps: float = 1e-5):
+    """Eval-mode BatchNorm1d after the depthwise conv folded into its weights (gigaam/encoder.py:402-405)."""
+    s = gamma / torch.sqrt(var + eps)
+    return dw_w * s[:, None], (dw_b - mean) * s + beta
+
+
+def pack_conv2_weight(w2: Tensor) -> Tensor:
+    """[C_out, C_in, kt, kf] -> [C_out, (kt, kf, C_in)]: K order of the implicit GEMM (tap-major, channel-minor)."""
+    return w2.permute(0, 2, 3, 1).reshape(w2.shape[0], -1)
+
+
+def pack_sub_out_weight(wo: Tensor, channels: int) -> Tensor:
+    """pre_encode.out.weight [d, C*F2] with K index c*F2+f (gigaam/encoder.py:125-127) -> K index f*C+c, the order in
+    which the stage-2 conv epilogue writes its [B, T', F2, C] output."""
+    f2 = wo.shape[1] // channels
+    return wo.reshape(wo.shape[0], channels, f2).permute(0, 2, 1).reshape(wo.shape[0], f2 * channels)
+
+
+def rotary_half_tables(dk: int, base: float, max_len: int):
+    """cos/sin [max_len, dk/2] of t * base^(-2i/dk) (gigaam/encoder.py:342-355; base = pos_emb_max_len)."""
+    inv_freq = 1.0 / (base ** (torch.arange(0, dk, 2).float() / dk))
+    freqs = torch.einsum("i,j->ij", torch.arange(max_len).float(), inv_freq)
+    return freqs.cos(), freqs.sin()
+
+
 class Engine:
     """One model replica on one CUDA device."""
 
@@ -112,21 +145,18 @@ class Engine:
         gw.sub1_w = self._dev(w1.reshape(d, 9))
         gw.sub1_b = self._dev(sd[p + "conv.0.bias"].float())
         w2 = sd[p + "conv.2.weight"].float()                     # [C_out, C_in, kt, kf]
-        gw.sub2_w = self._dev(w2.permute(0, 2, 3, 1).reshape(d, 9 * d), torch.float16)
+        gw.sub2_w = self._dev(pack_conv2_weight(w2), torch.float16)
         gw.sub2_b = self._dev(sd[p + "conv.2.bias"].float())
         wo = sd[p + "out.weight"].float()                        # [d, C*F2] with K index c*F2 + f
-        f2 = wo.shape[1] // d
-        gw.sub_out_w = self._dev(wo.reshape(d, d, f2).permute(0, 2, 1).reshape(d, f2 * d), torch.float16)
+        gw.sub_out_w = self._dev(pack_sub_out_weight(wo, d), torch.float16)
         gw.sub_out_b = self._dev(sd[p + "out.bias"].float())
 
     def _pack_rope(self, gw, enc):
         dk = self.d_model // self.n_heads
         base = enc["pos_emb_max_len"]  # the reference passes pos_emb_max_len as the rotary base (encoder.py:546-548)
-        inv_freq = 1.0 / (base ** (torch.arange(0, dk, 2).float() / dk))
-        t = torch.arange(enc["pos_emb_max_len"]).float()
-        freqs = torch.einsum("i,j->ij", t, inv_freq)             # [max_len, dk/2]
-        gw.rope_cos = self._dev(freqs.cos())
-        gw.rope_sin = self._dev(freqs.sin())
+        cos, sin = rotary_half_tables(dk, base, enc["pos_emb_max_len"])
+        gw.rope_cos = self._dev(cos)
+        gw.rope_sin = self._dev(sin)
 
     def _pack_layer(self, lw, sd, l: int, enc):
         q = f"encoder.layers.{l}."
@@ -146,17 +176,14 @@ class Engine:
         lw.w_o, lw.b_o = self._dev(f("self_attn.linear_out.weight"), h16), self._dev(f("self_attn.linear_out.bias"))
         lw.ln_conv_g, lw.ln_conv_b = self._dev(f("norm_conv.weight")), self._dev(f("norm_conv.bias"))
         # GLU pairing: accumulator tile j (256 columns) = [value rows j*128.. | gate rows d + j*128..]
-        half = 128
-        perm = torch.cat([torch.cat([torch.arange(j * half, (j + 1) * half), d + torch.arange(j * half, (j + 1) * half)])
-                          for j in range(d // half)])
+        perm = glu_row_permutation(d)
         w1 = f("conv.pointwise_conv1.weight").reshape(2 * d, d)
         lw.pw1_w, lw.pw1_b = self._dev(w1[perm], h16), self._dev(f("conv.pointwise_conv1.bias")[perm])
         dw = f("conv.depthwise_conv.weight").reshape(d, -1)
         db = f("conv.depthwise_conv.bias")
         if enc["conv_norm_type"] == "batch_norm":
-            s = f("conv.batch_norm.weight") / torch.sqrt(f("conv.batch_norm.running_var") + 1e-5)
-            dw = dw * s[:, None]
-            db = (db - f("conv.batch_norm.running_mean")) * s + f("conv.batch_norm.bias")
+            dw, db = fold_batchnorm(dw, db, f("conv.batch_norm.weight"), f("conv.batch_norm.bias"),
+                                    f("conv.batch_norm.running_mean"), f("conv.batch_norm.running_var"))
             lw.cn_g, lw.cn_b = None, None
         else:
             lw.cn_g, lw.cn_b = self._dev(f("conv.batch_norm.weight")), self._dev(f("conv.batch_norm.bias"))
@@ -259,6 +286,17 @@ class Engine:
                 frames.data_ptr(), counts.data_ptr(), max_out, self._stream())
         _lib.check(self.lib, self.handle, rc, "gam_greedy")
         return ids, frames, counts
+
+    def profile_begin(self) -> None:
+        _lib.check(self.lib, self.handle, self.lib.gam_profile_begin(self.handle), "gam_profile_begin")
+
+    def profile_end(self) -> Dict[str, Tuple[float, int]]:
+        """{kernel class: (total ms, launches)} measured with CUDA events since profile_begin()."""
+        n = int(self.lib.gam_profile_class_count())
+        ms = (C.c_double * n)()
+        cnt = (C.c_int64 * n)()
+        _lib.check(self.lib, self.handle, self.lib.gam_profile_end(self.handle, ms, cnt, n), "gam_profile_end")
+        return {self.lib.gam_profile_class_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(n) if cnt[i] > 0}
 
     def launch_count(self) -> int:
         return int(self.lib.gam_launch_count(self.handle))

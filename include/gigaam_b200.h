@@ -147,6 +147,15 @@ int gam_test_attention(gam_handle* h, const void* qkv, const int32_t* klen, void
 /* number of kernels this handle has launched so far (bench.py's gpu_launches) */
 int64_t gam_launch_count(const gam_handle* h);
 
+/* Optional per-launch timing with CUDA events on the launching stream (bench.py's roofline leg).
+ * gam_profile_begin() arms it; every kernel launched through this handle until gam_profile_end() is bracketed
+ * by an event pair; gam_profile_end() synchronises the events and returns summed milliseconds and launch
+ * counts per kernel class (gam_profile_class_name()).  Must not be armed during CUDA-graph capture. */
+int gam_profile_begin(gam_handle* h);
+int gam_profile_end(gam_handle* h, double* ms_per_class, int64_t* launches_per_class, int32_t n_classes);
+int gam_profile_class_count(void);
+const char* gam_profile_class_name(int32_t cls);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,166 @@
+"""CPU tests of the host side: C-ABI library loads and exports every declared symbol, weight re-layout functions
+are exact, the Python surface mirrors the reference's keys / signatures / error behaviour, and compute refuses to
+run without a GPU (no CPU fallback)."""
+import ctypes
+import inspect
+import re
+from pathlib import Path
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import gigaam_b200 as gigaam
+from gigaam_b200 import _lib, engine, synthetic
+from gigaam_b200.decoding import Tokenizer
+from gigaam_b200.timestamps_utils import compute_frame_shift, frames_to_words
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def test_library_exports_every_declared_symbol():
+    header = (ROOT / "include" / "gigaam_b200.h").read_text()
+    declared = set(re.findall(r"\b(gam_[a-z0-9_]+)\s*\(", header))
+    assert {"gam_create", "gam_logmel", "gam_encode", "gam_ctc_greedy", "gam_rnnt_greedy"} <= declared
+    lib = _lib.load()
+    for sym in sorted(declared):
+        assert hasattr(lib, sym), f"{sym} declared in include/gigaam_b200.h but not exported"
+    assert set(_lib.EXPORTS) == declared
+    assert lib.gam_version() >= 100
+    assert lib.gam_profile_class_count() > 10
+
+
+def test_struct_layouts_match_header():
+    header = (ROOT / "include" / "gigaam_b200.h").read_text()
+    layer = header[header.index("typedef struct gam_layer_weights"): header.index("} gam_layer_weights;")]
+    names = re.findall(r"[\*\s](\w+)\s*[;,]", re.sub(r"/\*.*?\*/", "", layer, flags=re.S))
+    assert tuple(names) == _lib.LAYER_FIELDS
+    assert ctypes.sizeof(_lib.GamLayerWeights) == 8 * len(_lib.LAYER_FIELDS)
+    cfg = header[header.index("typedef struct gam_config"): header.index("} gam_config;")]
+    cfg_names = re.findall(r"(\w+)\s*[;,]", re.sub(r"/\*.*?\*/", "", cfg, flags=re.S))
+    assert cfg_names == [n for n, _ in _lib.GamConfig._fields_]
+
+
+def test_no_cpu_fallback():
+    ck = gigaam.synthetic_checkpoint("v2_ctc", n_layers=1)
+    model = gigaam.load_model("v2_ctc", device="cpu", checkpoint=ck)
+    with pytest.raises(RuntimeError, match="no CPU"):
+        model(torch.zeros(1, 16000), torch.tensor([16000]))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        engine.Engine(ck["cfg"], ck["state_dict"], torch.device("cpu"))
+
+
+def test_state_dict_keys_and_first_parameter_match_reference_schema():
+    for name, cls in [("v2_ctc", gigaam.GigaAMASR), ("v2_rnnt", gigaam.GigaAMASR), ("v2_ssl", gigaam.GigaAM)]:
+        ck = gigaam.synthetic_checkpoint(name, n_layers=2)
+        model = gigaam.load_model(name, device="cpu", checkpoint=ck)
+        assert type(model) is cls
+        assert list(model.state_dict().keys()) == list(ck["state_dict"].keys()) or set(model.state_dict()) == set(ck["state_dict"])
+        assert next(iter(model.named_parameters()))[0] == "encoder.pre_encode.conv.0.weight"  # -> _dtype / _device
+        for k, v in model.state_dict().items():
+            assert torch.equal(v, ck["state_dict"][k]), k
+    # SURVEY Appendix B spot checks
+    sd = gigaam.synthetic_checkpoint("v2_rnnt", n_layers=1)["state_dict"]
+    assert sd["encoder.pre_encode.out.weight"].shape == (768, 12288)
+    assert sd["encoder.layers.0.conv.pointwise_conv1.weight"].shape == (1536, 768, 1)
+    assert sd["head.decoder.lstm.weight_ih_l0"].shape == (1280, 320)
+    assert sd["head.joint.joint_net.1.weight"].shape == (34, 320)
+    assert sd["preprocessor.featurizer.0.mel_scale.fb"].shape == (201, 64)
+
+
+def test_load_model_signature_and_errors():
+    sig = inspect.signature(gigaam.load_model)
+    assert list(sig.parameters)[:5] == ["model_name", "fp16_encoder", "use_flash", "device", "download_root"]
+    assert sig.parameters["fp16_encoder"].default is True and sig.parameters["use_flash"].default is False
+    with pytest.raises(ValueError, match="not found"):
+        gigaam.load_model("v9_ctc", device="cpu")
+    with pytest.raises(FileNotFoundError):
+        gigaam.load_model("v2_ctc", device="cpu", download_root="/nonexistent")
+
+
+def test_glu_permutation_and_bn_fold_are_exact():
+    d = 768
+    perm = engine.glu_row_permutation(d)
+    assert sorted(perm.tolist()) == list(range(2 * d))
+    g = torch.Generator().manual_seed(0)
+    w1 = torch.randn(2 * d, d, generator=g)
+    x = torch.randn(5, d, generator=g)
+    y = x @ w1[perm].t()                                           # accumulator column order
+    t = y.view(5, d // 128, 2, 128)
+    glu_tiles = (t[:, :, 0] * torch.sigmoid(t[:, :, 1])).reshape(5, d)
+    assert torch.allclose(glu_tiles, F.glu(x @ w1.t(), dim=-1), atol=1e-5)
+    # BatchNorm folding == conv -> batch_norm(eval)
+    k = 31
+    dw, db = torch.randn(d, k, generator=g), torch.randn(d, generator=g)
+    gamma, beta = torch.randn(d, generator=g), torch.randn(d, generator=g)
+    mean, var = torch.randn(d, generator=g), torch.rand(d, generator=g) + 0.1
+    xin = torch.randn(2, d, 40, generator=g)
+    ref = F.batch_norm(F.conv1d(xin, dw[:, None], db, padding=15, groups=d), mean, var, gamma, beta, False, 0.0, 1e-5)
+    fw, fb = engine.fold_batchnorm(dw, db, gamma, beta, mean, var)
+    assert torch.allclose(F.conv1d(xin, fw[:, None], fb, padding=15, groups=d), ref, atol=1e-4)
+
+
+def test_conv2_and_linear_permutations_reproduce_reference_ops():
+    """Implicit-GEMM K order (tap, channel) and the (f, c) flatten order give the reference's conv2d + Linear."""
+    g = torch.Generator().manual_seed(1)
+    C, F1, T1 = 8, 6, 9
+    x = torch.randn(2, C, T1, F1, generator=g)                     # [B, C, T, F] as the reference's conv sees it
+    w2 = torch.randn(C, C, 3, 3, generator=g)
+    ref = F.conv2d(x, w2, stride=2, padding=1)                     # [B, C, T2, F2]
+    T2, F2 = ref.shape[2], ref.shape[3]
+    xp = F.pad(x, (1, 1, 1, 1))
+    rows = []
+    for t2 in range(T2):
+        for f2 in range(F2):
+            taps = [xp[:, :, 2 * t2 + kt, 2 * f2 + kf] for kt in range(3) for kf in range(3)]   # each [B, C]
+            rows.append(torch.cat(taps, dim=1))
+    A = torch.stack(rows, 1)                                       # [B, T2*F2, 9C]
+    out = A @ engine.pack_conv2_weight(w2).t()
+    assert torch.allclose(out.view(2, T2, F2, C).permute(0, 3, 1, 2), ref, atol=1e-4)
+    wo = torch.randn(5, C * F2, generator=g)
+    y_ref = F.linear(ref.transpose(1, 2).reshape(2, T2, -1), wo)   # reference flatten: index c*F2 + f
+    y = out.view(2, T2, F2 * C) @ engine.pack_sub_out_weight(wo, C).t()
+    assert torch.allclose(y, y_ref, atol=1e-4)
+
+
+def test_length_arithmetic_matches_reference_formulae():
+    from gigaam_b200.encoder import StridingSubsampling
+    from gigaam_b200.preprocess import FeatureExtractor
+    fe = FeatureExtractor(16000, 64)
+    n = torch.tensor([80000, 160000, 240000, 400000, 3200, 5000, 399, 1])
+    assert fe.out_len(n).tolist() == [501, 1001, 1501, 2501, 21, 32, 3, 1]
+    sub = StridingSubsampling("conv2d", 3)
+    assert sub.calc_output_length(fe.out_len(n)).tolist() == [126, 251, 376, 626, 6, 8, 1, 1]
+    fe3 = FeatureExtractor(16000, 64, win_length=320, n_fft=320, hop_length=160, center=False)
+    assert fe3.out_len(torch.tensor([160000])).tolist() == [999]
+    assert StridingSubsampling("conv1d", 5).calc_output_length(torch.tensor([999])).tolist() == [250]
+
+
+def test_frontend_buffers_match_torchaudio():
+    ta = pytest.importorskip("torchaudio")
+    ms = ta.transforms.MelSpectrogram(sample_rate=16000, n_mels=64, win_length=400, hop_length=160, n_fft=400)
+    assert torch.allclose(synthetic.hann_window(400), ms.spectrogram.window, atol=1e-7)
+    assert torch.allclose(synthetic.mel_filterbank(201, 64, 16000), ms.mel_scale.fb, atol=1e-6)
+
+
+def test_tokenizer_and_word_timestamps():
+    tok = Tokenizer(list("ab c"))
+    assert len(tok) == 4 and tok.decode([0, 1, 2, 3]) == "ab c" and tok.id_to_str(2) == " "
+    words = frames_to_words(tok, [0, 1, 2, 3], [2, 3, 5, 9], compute_frame_shift(16000, 25))
+    assert [w.text for w in words] == ["ab", "c"]
+    assert words[0].start == pytest.approx(0.08) and words[0].end == pytest.approx(0.16)
+    assert words[1].start == pytest.approx(0.36) and words[1].end == pytest.approx(0.40)
+
+
+def test_synthetic_audio_is_deterministic_and_bounded():
+    a, la = synthetic.synthetic_audio(3, 1.0, seed=5, ragged=True)
+    b, lb = synthetic.synthetic_audio(3, 1.0, seed=5, ragged=True)
+    assert torch.equal(a, b) and torch.equal(la, lb)
+    assert a.dtype == torch.float32 and float(a.abs().max()) <= 1.1
+    assert la[0] == 16000 and (la[1:] < 16000).all()
+    assert float(a[1, int(la[1]):].abs().max()) == 0.0
+
+
+def test_transcription_result_str():
+    r = gigaam.TranscriptionResult(text="привет")
+    assert str(r) == "привет" and r.words is None

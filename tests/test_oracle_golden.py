@@ -1,0 +1,82 @@
+"""The CPU oracle (oracle/gigaam_oracle.py) against golden vectors produced by the REAL reference modules
+(oracle/make_golden.py, run where /root/reference exists).  This is what pins the oracle; the reference itself
+cannot travel to the GPU box."""
+import numpy as np
+import pytest
+import torch
+
+from gigaam_b200 import synthetic
+from oracle import gigaam_oracle as orc
+
+
+def _inputs(g):
+    wav, wav_len = synthetic.synthetic_audio(int(g["batch"]), float(g["seconds"]), seed=int(g["wav_seed"]), ragged=bool(g["ragged"]))
+    assert np.array_equal(wav_len.numpy(), g["wav_len"])
+    return wav, wav_len
+
+
+def _rel(a, b):
+    return float((a - b).norm() / b.norm())
+
+
+@pytest.fixture(scope="module")
+def ctc_case(golden_dir, v2_ctc_ckpt):
+    g = np.load(golden_dir / "v2_ctc_b2_2s.npz")
+    wav, wav_len = _inputs(g)
+    cfg, sd = v2_ctc_ckpt["cfg"], v2_ctc_ckpt["state_dict"]
+    with torch.inference_mode():
+        mel = orc.log_mel(wav, sd, cfg["preprocessor"])
+        mel_len = orc.logmel_out_len(wav_len, 160, 400, True)
+        enc, enc_len, stages = orc.encoder_forward(mel, mel_len, sd, cfg["encoder"], return_all=True)
+    return g, cfg, sd, mel, mel_len, enc, enc_len, stages
+
+
+def test_logmel_matches_reference(ctc_case):
+    g, _, _, mel, mel_len, *_ = ctc_case
+    assert np.array_equal(mel_len.numpy(), g["mel_len"])
+    assert float((mel - torch.from_numpy(g["mel"])).abs().max()) < 1e-4
+
+
+def test_pre_encode_and_encoder_match_reference(ctc_case):
+    g, _, _, _, _, enc, enc_len, stages = ctc_case
+    assert np.array_equal(enc_len.numpy(), g["enc_len"])
+    valid = torch.arange(enc.shape[2])[None, :] < enc_len[:, None]
+    assert _rel(stages[0][valid], torch.from_numpy(g["pre_encode"])[valid]) < 1e-5
+    assert _rel(enc.transpose(1, 2)[valid], torch.from_numpy(g["enc"]).transpose(1, 2)[valid]) < 1e-5
+
+
+def test_ctc_greedy_matches_reference(ctc_case):
+    g, _, sd, *_ = ctc_case
+    hyp = orc.ctc_greedy(torch.from_numpy(g["enc"]), torch.from_numpy(g["enc_len"]), sd)
+    for b, (ids, frames) in enumerate(hyp):
+        assert ids == g[f"ids_{b}"].tolist()
+        assert frames == g[f"frames_{b}"].tolist()
+
+
+def test_rnnt_greedy_matches_reference(golden_dir, v2_rnnt_ckpt):
+    g = np.load(golden_dir / "v2_rnnt_b2_2s.npz")
+    hyp = orc.rnnt_greedy(torch.from_numpy(g["enc"]), torch.from_numpy(g["enc_len"]), v2_rnnt_ckpt["state_dict"], 10)
+    total = 0
+    for b, (ids, frames) in enumerate(hyp):
+        assert ids == g[f"ids_{b}"].tolist()
+        assert frames == g[f"frames_{b}"].tolist()
+        total += len(ids)
+    assert total > 0  # the calibrated blank bias must leave a non-degenerate hypothesis
+
+
+def test_ctc_collapse_edge_cases(v2_ctc_ckpt):
+    """Empty lengths, length 1, repeated labels, all blanks (gigaam/decoding.py:76-91 semantics)."""
+    sd = v2_ctc_ckpt["state_dict"]
+    V1 = sd["head.decoder_layers.0.bias"].numel()
+    W = sd["head.decoder_layers.0.weight"].reshape(V1, -1)
+    # craft encoder rows that make the head emit chosen labels: e = pinv(W) one-hot * big
+    pinv = torch.linalg.pinv(W)
+    labels = torch.tensor([[3, 3, V1 - 1, 3, 5, 5, 5, V1 - 1], [V1 - 1] * 8, [1, 2, 3, 4, 5, 6, 7, 8]])
+    onehot = torch.nn.functional.one_hot(labels, V1).float() * 50.0
+    enc = (onehot @ pinv.t()).transpose(1, 2)                      # [B, d, T]
+    got = orc.ctc_greedy(enc, torch.tensor([8, 8, 0]), sd)
+    assert got[0] == ([3, 3, 5], [0, 3, 4])
+    assert got[1] == ([], [])
+    assert got[2] == ([], [])
+    got = orc.ctc_greedy(enc, torch.tensor([1, 1, 3]), sd)
+    assert got[0] == ([3], [0]) and got[2] == ([1, 2, 3], [0, 1, 2])
