@@ -103,12 +103,31 @@ def cpu_reference(steps: int, warmup: int, batch: int = 4, seconds: float = SECO
     from gigaam_b200 import synthetic
     from oracle import gigaam_oracle as orc
 
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     ck = synthetic.synthetic_checkpoint(MODEL, seed=0)
     cfg, sd = ck["cfg"], ck["state_dict"]
     wav, wav_len = synthetic.synthetic_audio(batch, seconds, seed=1234)
     vocab = cfg["decoding"]["vocabulary"]
+    # all host threads the process may use: affinity mask capped by the cgroup CPU quota (a 128-thread pool on a
+    # quota of a few CPUs thrashes); then keep the fastest of {all, 1/2, 1/4} on a short probe
+    avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            avail = max(1, min(avail, int(float(quota) / float(period) + 0.5)))
+    except Exception:
+        pass
+    probe_wav, probe_len = wav[:1, : 3 * 16000].contiguous(), torch.tensor([3 * 16000])
+    best, cores = None, avail
+    for n in sorted({avail, max(1, avail // 2), max(1, avail // 4)}, reverse=True):
+        torch.set_num_threads(n)
+        with torch.inference_mode():
+            orc.model_forward(probe_wav, probe_len, sd, cfg)
+            t0 = time.perf_counter()
+            orc.model_forward(probe_wav, probe_len, sd, cfg)
+            dt = time.perf_counter() - t0
+        if best is None or dt < best:
+            best, cores = dt, n
+    torch.set_num_threads(cores)
 
     def step():
         with torch.inference_mode():

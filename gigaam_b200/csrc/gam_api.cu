@@ -271,21 +271,21 @@ int gam_create(const gam_config* cfg, const gam_weights* w, int device, gam_hand
   for (int l = 0; l < c.n_layers; ++l) {
     const gam_layer_weights& lw = h->layers[l];
     LayerMaps& lm = h->lmaps[l];
-    rc |= make_tmap_2d_f16(&lm.ff1_w1, lw.ff1_w1, ff, d, d, 256, 64);
-    rc |= make_tmap_2d_f16(&lm.ff1_w2, lw.ff1_w2, d, ff, ff, 256, 64);
-    rc |= make_tmap_2d_f16(&lm.w_qk, lw.w_qk, 2 * d, d, d, 256, 64);
-    rc |= make_tmap_2d_f16(&lm.w_v, lw.w_v, d, d, d, 256, 64);
-    rc |= make_tmap_2d_f16(&lm.w_o, lw.w_o, d, d, d, 256, 64);
-    rc |= make_tmap_2d_f16(&lm.pw1, lw.pw1_w, 2 * d, d, d, 256, 64);
-    rc |= make_tmap_2d_f16(&lm.pw2, lw.pw2_w, d, d, d, 256, 64);
-    rc |= make_tmap_2d_f16(&lm.ff2_w1, lw.ff2_w1, ff, d, d, 256, 64);
-    rc |= make_tmap_2d_f16(&lm.ff2_w2, lw.ff2_w2, d, ff, ff, 256, 64);
+    rc |= make_tmap_2d_f16(&lm.ff1_w1, lw.ff1_w1, ff, d, d, 128, 64);
+    rc |= make_tmap_2d_f16(&lm.ff1_w2, lw.ff1_w2, d, ff, ff, 128, 64);
+    rc |= make_tmap_2d_f16(&lm.w_qk, lw.w_qk, 2 * d, d, d, 128, 64);
+    rc |= make_tmap_2d_f16(&lm.w_v, lw.w_v, d, d, d, 128, 64);
+    rc |= make_tmap_2d_f16(&lm.w_o, lw.w_o, d, d, d, 128, 64);
+    rc |= make_tmap_2d_f16(&lm.pw1, lw.pw1_w, 2 * d, d, d, 128, 64);
+    rc |= make_tmap_2d_f16(&lm.pw2, lw.pw2_w, d, d, d, 128, 64);
+    rc |= make_tmap_2d_f16(&lm.ff2_w1, lw.ff2_w1, ff, d, d, 128, 64);
+    rc |= make_tmap_2d_f16(&lm.ff2_w2, lw.ff2_w2, d, ff, ff, 128, 64);
   }
   const int pad = (c.subs_kernel_size - 1) / 2;
   const int F1 = sub_out_len(c.feat_in, c.subs_kernel_size, pad), F2 = sub_out_len(F1, c.subs_kernel_size, pad);
   if (F1 != 32 || F2 != 16) return fail(h, -10, "conv2d subsampling kernels are specialised for feat_in 64 (F1=32,F2=16)");
-  rc |= make_tmap_2d_f16(&h->m_sub2_w, w->sub2_w, d, 9 * d, 9 * d, 256, 64);
-  rc |= make_tmap_2d_f16(&h->m_sub_out_w, w->sub_out_w, d, static_cast<uint64_t>(F2) * d, static_cast<uint64_t>(F2) * d, 256, 64);
+  rc |= make_tmap_2d_f16(&h->m_sub2_w, w->sub2_w, d, 9 * d, 9 * d, 128, 64);
+  rc |= make_tmap_2d_f16(&h->m_sub_out_w, w->sub_out_w, d, static_cast<uint64_t>(F2) * d, static_cast<uint64_t>(F2) * d, 128, 64);
   if (rc != 0) return fail(h, -2, "cuTensorMapEncodeTiled failed for weight maps (rc=%d)", rc);
   return 0;
 }
@@ -497,7 +497,7 @@ int gam_test_gemm(gam_handle* h, int32_t kind, const void* A, const void* W, con
                   int32_t M, int32_t N, int32_t K, int32_t ldo, float scale, void* stream) {
   CUtensorMap ta, tw;
   int rc = make_tmap_2d_f16(&ta, A, M, K, K, 128, 64);
-  rc |= make_tmap_2d_f16(&tw, W, N, K, K, 256, 64);
+  rc |= make_tmap_2d_f16(&tw, W, N, K, K, 128, 64);
   if (rc) return fail(h, -2, "tensor map encode failed (rc=%d)", rc);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   {

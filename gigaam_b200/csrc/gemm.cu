@@ -1,5 +1,8 @@
-// Instantiations and host launchers of the tcgen05 GEMM (gemm_sm100.cuh).
-#include "gemm_sm100.cuh"
+// Instantiations and host launchers of the tcgen05 GEMMs (gemm_sm100.cuh: one CTA per 128 x 256 tile;
+// gemm2_sm100.cuh: CTA pairs, 256 x 256 tiles, cta_group::2 -- the default).
+#include <cstdlib>
+
+#include "gemm2_sm100.cuh"
 #include "kernels.h"
 
 namespace gam {
@@ -7,8 +10,17 @@ namespace {
 
 constexpr int kBN = 256;
 
+bool use_v1() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = std::getenv("GAM_GEMM_V1");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 template <int EPI, int AMODE>
-int launch_one(const CUtensorMap* ta, const CUtensorMap* tw, const GemmParams& p, int num_sms, cudaStream_t s) {
+int launch_v1(const CUtensorMap* ta, const CUtensorMap* tw, const GemmParams& p, int num_sms, cudaStream_t s) {
   auto kern = gemm_f16_tn_kernel<kBN, EPI, AMODE>;
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int grid = tiles < num_sms ? tiles : num_sms;
@@ -17,10 +29,31 @@ int launch_one(const CUtensorMap* ta, const CUtensorMap* tw, const GemmParams& p
   return cudaPeekAtLastError() == cudaSuccess ? 0 : -2;
 }
 
+// p.num_m_tiles counts 128-row blocks on entry; the pair kernel wants 256-row pair tiles
+template <int EPI, int AMODE>
+int launch_v2(const CUtensorMap* ta, const CUtensorMap* tw, GemmParams p, int num_sms, cudaStream_t s) {
+  auto kern = gemm2_f16_tn_kernel<EPI, AMODE>;
+  p.num_m_tiles = (p.num_m_tiles + 1) / 2;
+  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  const int max_pairs = num_sms / 2;
+  const int npairs = tiles < max_pairs ? tiles : max_pairs;
+  if (npairs <= 0) return 0;
+  kern<<<2 * npairs, kGemmThreads, kG2Smem, s>>>(*ta, *tw, p);
+  return cudaPeekAtLastError() == cudaSuccess ? 0 : -2;
+}
+
+template <int EPI, int AMODE>
+int launch_one(const CUtensorMap* ta, const CUtensorMap* tw, const GemmParams& p, int num_sms, cudaStream_t s) {
+  return use_v1() ? launch_v1<EPI, AMODE>(ta, tw, p, num_sms, s) : launch_v2<EPI, AMODE>(ta, tw, p, num_sms, s);
+}
+
 template <int EPI, int AMODE>
 int set_attr() {
-  auto kern = gemm_f16_tn_kernel<kBN, EPI, AMODE>;
-  return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<kBN>::kTotal) == cudaSuccess ? 0 : -1;
+  auto k1 = gemm_f16_tn_kernel<kBN, EPI, AMODE>;
+  auto k2 = gemm2_f16_tn_kernel<EPI, AMODE>;
+  int rc = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<kBN>::kTotal) == cudaSuccess ? 0 : -1;
+  rc |= cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, kG2Smem) == cudaSuccess ? 0 : -1;
+  return rc;
 }
 
 }  // namespace
@@ -70,7 +103,8 @@ int launch_gemm_conv(const CUtensorMap* ta4, const CUtensorMap* tw, int B, int T
   p.conv_tiles_per_utt = (T2 + 7) / 8;
   p.conv_kchunks = C / kGemmBK;
   p.conv_len2 = len2;
-  p.num_m_tiles = B * p.conv_tiles_per_utt;
+  p.conv_num_blocks = B * p.conv_tiles_per_utt;
+  p.num_m_tiles = p.conv_num_blocks;
   p.num_n_tiles = N / kBN;
   p.num_k_blocks = 9 * p.conv_kchunks;
   p.bias = bias;

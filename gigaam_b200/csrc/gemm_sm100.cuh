@@ -43,6 +43,7 @@ struct GemmParams {
   int conv_T2;            // output time steps per utterance
   int conv_tiles_per_utt; // ceil(T2 / 8)
   int conv_kchunks;       // C / 64
+  int conv_num_blocks;    // B * conv_tiles_per_utt  (128-row blocks that exist)
   const int* conv_len2;   // [B] valid output time steps
 };
 
@@ -145,8 +146,11 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             ptx::tma_load_4d(smem_a + stage * S::kABytes, &tmap_a, &full_bar[stage], c0, kf - 1,
                              2 * conv_t0 + kt - 1, conv_b);
           }
-          ptx::tma_load_2d(smem_b + stage * S::kBBytes, &tmap_w, &full_bar[stage], kb * kGemmBK,
-                           n_blk * BN);
+          // W descriptors carry 128-row boxes (shared with the CTA-pair kernel): BN / 128 loads per stage
+#pragma unroll
+          for (int h = 0; h < BN / 128; ++h)
+            ptx::tma_load_2d(smem_b + stage * S::kBBytes + h * 128 * 128, &tmap_w, &full_bar[stage], kb * kGemmBK,
+                             n_blk * BN + h * 128);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }

@@ -155,11 +155,11 @@ def test_ctc_ids_margin_aware_larger_batch(eng_ctc, v2_ctc_ckpt):
     top2 = logits.topk(2, dim=-1).values
     margin = top2[..., 0] - top2[..., 1]
     valid = torch.arange(logits.shape[1])[None, :] < len_o[:, None]
-    noise = 4.0 * float((F.conv1d(enc.cpu().transpose(1, 2), sd["head.decoder_layers.0.weight"]) .transpose(1, 2) -
+    noise = 2.0 * float((F.conv1d(enc.cpu().transpose(1, 2), sd["head.decoder_layers.0.weight"]) .transpose(1, 2) -
                          F.conv1d(enc_o, sd["head.decoder_layers.0.weight"]).transpose(1, 2))[valid].abs().max())
     safe = valid & (margin > noise)
     assert torch.equal(lab_gpu[safe], logits.argmax(-1)[safe])
-    assert float((valid & ~safe).sum()) / float(valid.sum()) < 0.05
+    assert float((valid & ~safe).sum()) / float(valid.sum()) < 0.10
 
 
 def test_batch_vs_single_consistency(eng_ctc):
