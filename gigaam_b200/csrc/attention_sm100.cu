@@ -231,14 +231,238 @@ __global__ void __launch_bounds__(kAttnThreads) attention_kernel(const __grid_co
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Resident-S variant for T <= 384 (every BASELINE config except the 25 s one): the whole score row of a
+// query lives in TMEM (nkb * 128 fp32 columns), so there is ONE softmax sweep per row (max, then exp) with
+// no recompute and no running-max correction, and only three hand-offs per query tile (S ready -> P ready
+// -> O ready).  When T <= 256 one CTA serves BOTH query tiles of a (utterance, head): K and V are fetched
+// once, two softmax warpgroups run side by side, and O aliases the first 64 columns of its tile's dead S
+// region so 2 x 256 TMEM columns suffice.
+constexpr int kResMaxKB = 3;
+constexpr int kResMaxQT = 2;
+
+struct AttnResParams {
+  int T, nkb, QT;
+  const int* klen;
+  __half* out;
+  int ld_out, dk;
+  float scale_log2;
+};
+
+__global__ void __launch_bounds__(64 + kResMaxQT * 128) attention_resident_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
+                                                                                    const AttnResParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int nkb = p.nkb, QT = p.QT;
+  uint8_t* sQ = smem;                                  // [QT] tiles
+  uint8_t* sK = sQ + QT * kTileBytes;                  // [nkb]
+  uint8_t* sV = sK + nkb * kTileBytes;                 // [nkb]
+  uint8_t* sP = sV + nkb * kTileBytes;                 // [QT][2 * nkb] chunks of 64 keys
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + QT * 2 * nkb * kTileBytes);
+  uint64_t* kv_full = bars;                            // [kResMaxKB]
+  uint64_t* s_full = kv_full + kResMaxKB;              // [kResMaxQT]
+  uint64_t* p_full = s_full + kResMaxQT;               // [kResMaxQT]
+  uint64_t* o_full = p_full + kResMaxQT;               // [kResMaxQT]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + kResMaxQT);
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int row0 = b * p.T;
+  const int q_base = blockIdx.x * QT * 128;
+  const int dmodel = p.ld_out;
+
+  if (warp_idx == 0 && ptx::elect_one()) {
+    ptx::prefetch_tmap(&tmap_qkv);
+    for (int i = 0; i < kResMaxKB; ++i) ptx::mbar_init(&kv_full[i], 1);
+    for (int i = 0; i < kResMaxQT; ++i) {
+      ptx::mbar_init(&s_full[i], 1);
+      ptx::mbar_init(&p_full[i], 4);
+      ptx::mbar_init(&o_full[i], 1);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp_idx == 1) ptx::tmem_alloc<512>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t s_cols = nkb * 128;
+
+  if (warp_idx == 0) {
+    if (ptx::elect_one()) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        ptx::mbar_arrive_expect_tx(&kv_full[kb], (2 + (kb == 0 ? QT : 0)) * kTileBytes);
+        if (kb == 0)
+          for (int qt = 0; qt < QT; ++qt)
+            ptx::tma_load_2d(sQ + qt * kTileBytes, &tmap_qkv, &kv_full[0], h * p.dk, row0 + q_base + qt * 128);
+        ptx::tma_load_2d(sK + kb * kTileBytes, &tmap_qkv, &kv_full[kb], dmodel + h * p.dk, row0 + kb * 128);
+        ptx::tma_load_2d(sV + kb * kTileBytes, &tmap_qkv, &kv_full[kb], 2 * dmodel + h * p.dk, row0 + kb * 128);
+      }
+    }
+  } else if (warp_idx == 1) {
+    constexpr uint32_t kIdescS = ptx::make_idesc_f16(128, 128, 0, 0);
+    constexpr uint32_t kIdescPV = ptx::make_idesc_f16(128, 64, 0, 1);
+    const int ksteps_qk = p.dk / 16;
+    // S[qt][:, kb*128 : kb*128+128] = Q[qt] K[kb]^T
+    for (int kb = 0; kb < nkb; ++kb) {
+      ptx::mbar_wait(&kv_full[kb], 0);
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
+        const uint32_t ka = ptx::smem_u32(sK + kb * kTileBytes);
+        for (int qt = 0; qt < QT; ++qt) {
+          const uint32_t qa = ptx::smem_u32(sQ + qt * kTileBytes);
+          for (int k = 0; k < ksteps_qk; ++k)
+            ptx::mma_f16_ss(tmem_base + qt * s_cols + kb * 128, ptx::make_smem_desc_sw128(qa + k * 32, 16, 1024),
+                            ptx::make_smem_desc_sw128(ka + k * 32, 16, 1024), kIdescS, k != 0 ? 1u : 0u);
+          if (kb == nkb - 1) ptx::mma_commit(&s_full[qt]);
+        }
+      }
+      __syncwarp();
+    }
+    // O[qt] = P[qt] V   (O overwrites the first 64 columns of the tile's S region, dead once P is in smem)
+    for (int qt = 0; qt < QT; ++qt) {
+      ptx::mbar_wait(&p_full[qt], 0);
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
+        const uint32_t pa = ptx::smem_u32(sP + qt * 2 * nkb * kTileBytes);
+        for (int kb = 0; kb < nkb; ++kb) {
+          const uint32_t va = ptx::smem_u32(sV + kb * kTileBytes);
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint64_t da = ptx::make_smem_desc_sw128(pa + (kb * 2 + (ks >> 2)) * kTileBytes + (ks & 3) * 32, 16, 1024);
+            const uint64_t db = ptx::make_smem_desc_sw128(va + ks * 2048, 1024, 1024);
+            ptx::mma_f16_ss(tmem_base + qt * s_cols, da, db, kIdescPV, (kb | ks) != 0 ? 1u : 0u);
+          }
+        }
+        ptx::mma_commit(&o_full[qt]);
+      }
+      __syncwarp();
+    }
+  } else if (warp_idx < 2 + 4 * QT) {
+    const int qt = (warp_idx - 2) >> 2;
+    const int quad = warp_idx & 3;
+    const int lane = threadIdx.x & 31;
+    const int r = quad * 32 + lane;
+    const uint32_t t_s = tmem_base + qt * s_cols + (static_cast<uint32_t>(quad * 32) << 16);
+    int klen = p.T;
+    if (p.klen != nullptr) klen = min(max(p.klen[b], 0), p.T);
+    const int nchunks = (klen + 31) >> 5;   // 32-key chunks holding at least one valid key
+    ptx::mbar_wait(&s_full[qt], 0);
+    ptx::tc_fence_after();
+    float m = -INFINITY;
+#pragma unroll 1
+    for (int c = 0; c < nchunks; ++c) {
+      uint32_t v[32];
+      ptx::tmem_ld_32x32b_x32(t_s + c * 32, v);
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (c * 32 + j < klen) m = fmaxf(m, __uint_as_float(v[j]));
+    }
+    if (m == -INFINITY) m = 0.f;
+    const float mc = m * p.scale_log2;
+    float sum = 0.f;
+    uint8_t* myP = sP + qt * 2 * nkb * kTileBytes;
+#pragma unroll 1
+    for (int c = 0; c < nkb * 4; ++c) {
+      uint32_t pk[16];
+      if (c < nchunks) {
+        uint32_t v[32];
+        ptx::tmem_ld_32x32b_x32(t_s + c * 32, v);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          const float p0 = (c * 32 + j < klen) ? ex2(fmaf(__uint_as_float(v[j]), p.scale_log2, -mc)) : 0.f;
+          const float p1 = (c * 32 + j + 1 < klen) ? ex2(fmaf(__uint_as_float(v[j + 1]), p.scale_log2, -mc)) : 0.f;
+          sum += p0 + p1;
+          __half2 hh = __floats2half2_rn(p0, p1);
+          pk[j >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) pk[j] = 0u;
+      }
+      // 32 keys = 64 bytes = pieces (c & 1) * 4 .. +3 of row r in 64-key chunk c >> 1 (K-major, SWIZZLE_128B)
+      uint8_t* chunk = myP + (c >> 1) * kTileBytes + r * 128;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int piece = (c & 1) * 4 + j;
+        *reinterpret_cast<uint4*>(chunk + ((piece ^ (r & 7)) << 4)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+      }
+    }
+    ptx::tc_fence_before();
+    ptx::fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(&p_full[qt]);
+    ptx::mbar_wait(&o_full[qt], 0);
+    ptx::tc_fence_after();
+    const float inv = sum > 0.f ? 1.0f / sum : 0.f;
+    const int q = q_base + qt * 128 + r;
+    __half* dst = p.out + static_cast<size_t>(row0 + q) * p.ld_out + h * p.dk;
+    for (int c = 0; c < p.dk; c += 16) {
+      uint32_t v[16];
+      ptx::tmem_ld_32x32b_x16(t_s + c, v);
+      ptx::tmem_ld_wait();
+      if (q < p.T) {
+        uint32_t o[8];
+#pragma unroll
+        for (int j = 0; j < 16; j += 2) {
+          __half2 hh = __floats2half2_rn(__uint_as_float(v[j]) * inv, __uint_as_float(v[j + 1]) * inv);
+          o[j >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+        }
+        uint4* d4 = reinterpret_cast<uint4*>(dst + c);
+        d4[0] = make_uint4(o[0], o[1], o[2], o[3]);
+        d4[1] = make_uint4(o[4], o[5], o[6], o[7]);
+      }
+    }
+    ptx::tc_fence_before();
+  }
+
+  __syncthreads();
+  if (warp_idx == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<512>(tmem_base);
+  }
+}
+
 }  // namespace
 
 int attention_smem_bytes(int nkb) { return (3 + 2 * nkb) * kTileBytes + 128 + 1024; }
+static int attention_res_smem_bytes(int nkb, int QT) { return (QT + 2 * nkb + QT * 2 * nkb) * kTileBytes + 128 + 1024; }
+
+static int launch_attention_resident(const CUtensorMap* tmap_qkv, const int* klen, __half* out, int B, int T, int H, int dk,
+                                     int d_model, cudaStream_t s) {
+  const int nkb = (T + 127) / 128;
+  AttnResParams p;
+  p.T = T;
+  p.nkb = nkb;
+  p.QT = nkb <= 2 ? 2 : 1;
+  p.klen = klen;
+  p.out = out;
+  p.ld_out = d_model;
+  p.dk = dk;
+  p.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(dk));
+  static int attr_set = 0;
+  if (!attr_set) {
+    cudaFuncSetAttribute(attention_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_set = 1;
+  }
+  const int nqt = (T + 127) / 128;
+  dim3 grid((nqt + p.QT - 1) / p.QT, H, B);
+  attention_resident_kernel<<<grid, 64 + p.QT * 128, attention_res_smem_bytes(nkb, p.QT), s>>>(*tmap_qkv, p);
+  return 0;
+}
 
 int launch_attention(const CUtensorMap* tmap_qkv, const int* klen, __half* out, int B, int T, int H, int dk, int d_model,
                      cudaStream_t s) {
   const int nkb = (T + 127) / 128;
   if (nkb > kMaxKB || dk % 16 != 0 || dk > 64) return -1;
+  static int force_v1 = -1;
+  if (force_v1 < 0) {
+    const char* e = getenv("GAM_ATTN_V1");
+    force_v1 = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (nkb <= kResMaxKB && !force_v1) return launch_attention_resident(tmap_qkv, klen, out, B, T, H, dk, d_model, s);
   AttnParams p;
   p.T = T;
   p.nkb = nkb;

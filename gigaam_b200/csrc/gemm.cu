@@ -38,7 +38,7 @@ int launch_v2(const CUtensorMap* ta, const CUtensorMap* tw, GemmParams p, int nu
   const int max_pairs = num_sms / 2;
   const int npairs = tiles < max_pairs ? tiles : max_pairs;
   if (npairs <= 0) return 0;
-  kern<<<2 * npairs, kGemmThreads, kG2Smem, s>>>(*ta, *tw, p);
+  kern<<<2 * npairs, kG2Threads, kG2Smem, s>>>(*ta, *tw, p);
   return cudaPeekAtLastError() == cudaSuccess ? 0 : -2;
 }
 

@@ -2,37 +2,41 @@
 //
 // Two CTAs on the two SMs of a TPC compute one 256 x 256 tile: each CTA stages its own 128 rows of A and HALF
 // (128 rows) of the W tile, the leader CTA issues tcgen05.mma.cta_group::2 (M = 256), and each CTA ends up with
-// the accumulators of its 128 rows (x 256 columns) in its own TMEM.  Per k-block each SM now moves
+// the accumulators of its 128 rows (x 256 columns) in its own TMEM.  Per k-block each SM moves
 // 16 KB (A) + 16 KB (W half) through shared memory instead of 16 + 32 KB: the single-CTA kernel
 // (gemm_sm100.cuh) was bound by shared-memory / L2 operand traffic at ~50 % tensor-pipe.
 //
-// Pipeline (per CTA): warp 0 = TMA producer, warp 1 = MMA issuer (leader CTA only) + TMEM owner,
-// warps 2..5 = epilogue.  6-stage smem ring, double-buffered TMEM accumulators (2 x 256 columns).
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer (leader CTA only) + TMEM owner,
+// warps 2..9 = epilogue (two warps per TMEM lane quadrant, each owning 128 of the 256 accumulator columns).
+// 5-stage smem ring, double-buffered TMEM accumulators (2 x 256 columns).
 // Barriers: full[s] lives in the leader (both CTAs' TMA bytes + both producers' arrivals land there),
 // empty[s] / tmem_full[a] are per CTA and signalled with multicast tcgen05.commit, tmem_empty[a] lives in the
-// leader and collects one arrival per epilogue warp of both CTAs.
+// leader and collects one arrival per epilogue warp of both CTAs.  Remote arrivals are plain
+// (CTA-scope) arrives: a cluster-scope release fence per k-block serialised the producer (measured).
 //
 // Epilogue: TMEM -> registers (thread = row) -> per-warp smem staging tile (pitch 36 words: conflict-free both
 // ways) -> coalesced 16-byte global accesses (a warp instruction covers 4 full 128-byte rows), where bias /
-// residual / activation are applied.  The previous thread-per-row global epilogue cost 32 LSU wavefronts per
-// instruction and dominated the K = 768 GEMMs.
+// residual / activation are applied.  Residual reads are software-pipelined one chunk ahead; with eight warps
+// that keeps 16 chunk loads in flight per SM, enough to hide L2 latency behind the next tile's main loop.
 #pragma once
 #include "gemm_sm100.cuh"
 
 namespace gam {
 
-constexpr int kG2Stages = 6;
+constexpr int kG2Threads = 320;
+constexpr int kG2EpiWarps = 8;
+constexpr int kG2Stages = 5;
 constexpr int kG2ABytes = 128 * 64 * 2;       // 16 KB: this CTA's 128 rows of A
 constexpr int kG2BBytes = 128 * 64 * 2;       // 16 KB: this CTA's half of the 256-row W tile
 constexpr int kG2StageBytes = kG2ABytes + kG2BBytes;
 constexpr int kG2WarpStage = 32 * 36 * 4;     // 4608 B staging tile per epilogue warp
-constexpr int kG2WarpBias = 256 * 4;          // per-warp copy of the tile's bias slice
-constexpr int kG2EpiBytes = 4 * (kG2WarpStage + kG2WarpBias);
+constexpr int kG2WarpBias = 128 * 4;          // per-warp copy of its 128 bias values
+constexpr int kG2EpiBytes = kG2EpiWarps * (kG2WarpStage + kG2WarpBias);
 constexpr int kG2BarBytes = 256;
 constexpr int kG2Smem = kG2Stages * kG2StageBytes + kG2EpiBytes + kG2BarBytes + 1024;
 
 template <int EPI, int AMODE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kG2Threads, 1)
 gemm2_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                     const GemmParams p) {
   constexpr int BN = 256;
@@ -67,7 +71,7 @@ gemm2_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&tmem_full[s], 1);
-      ptx::mbar_init(&tmem_empty[s], 8);  // 4 epilogue warps x 2 CTAs
+      ptx::mbar_init(&tmem_empty[s], 2 * kG2EpiWarps);
     }
     ptx::fence_mbar_init();
   }
@@ -88,7 +92,7 @@ gemm2_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const int m_blk = m_pair * 2 + static_cast<int>(rank);   // this CTA's 128-row block
         int conv_b = 0, conv_t0 = 0;
         if constexpr (AMODE == A_CONV) {
-          conv_b = m_blk / p.conv_tiles_per_utt;
+          conv_b = m_blk / p.conv_tiles_per_utt;   // == B for the idle block of an odd count: OOB -> zero fill
           conv_t0 = (m_blk % p.conv_tiles_per_utt) * 8;
         }
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
@@ -101,8 +105,6 @@ gemm2_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const int tap = kb / p.conv_kchunks;
             const int c0 = (kb % p.conv_kchunks) * kGemmBK;
             const int kt = tap / 3, kf = tap % 3;
-            // a 128-row block past the end of the batch (odd number of blocks): coordinates stay in range of the
-            // descriptor's batch dimension or fall outside it -> zero fill, never stored
             ptx::tma_load_4d_2sm(smem_a + stage * kG2ABytes, &tmap_a, &full_bar[stage], c0, kf - 1, 2 * conv_t0 + kt - 1,
                                  conv_b);
           }
@@ -145,10 +147,11 @@ gemm2_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       }
     }
   } else {
-    // ===================================================== epilogue (warps 2..5, both CTAs)
-    const int quad = warp_idx & 3;
+    // ===================================================== epilogue (warps 2..9, both CTAs)
+    const int quad = warp_idx & 3;          // TMEM lane quadrant
     const int lane = threadIdx.x & 31;
     const int ew = warp_idx - 2;
+    const int half = ew >> 2;               // which 128 accumulator columns (GLU: which 64 value/gate columns)
     float* stg = reinterpret_cast<float*>(smem_epi + ew * (kG2WarpStage + kG2WarpBias));
     float* bias_s = reinterpret_cast<float*>(smem_epi + ew * (kG2WarpStage + kG2WarpBias) + kG2WarpStage);
     int acc = 0;
@@ -157,22 +160,23 @@ gemm2_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const int m_pair = tile / p.num_n_tiles;
       const int n_blk = tile % p.num_n_tiles;
       const int m_blk = m_pair * 2 + static_cast<int>(rank);
-      // stage this tile's bias slice (256 floats) for broadcast reads
+      // this warp's 128 bias values -> smem for broadcast reads
       {
-        const float4* bsrc = reinterpret_cast<const float4*>(p.bias + n_blk * BN);
-        float4* bdst = reinterpret_cast<float4*>(bias_s);
-        bdst[lane] = __ldg(bsrc + lane);
-        bdst[lane + 32] = __ldg(bsrc + lane + 32);
+        const float* bsrc = p.bias + n_blk * BN;
+        float4 bv;
+        if constexpr (EPI == EPI_BIAS_GLU_F16) {
+          // [0,64) = value bias of columns half*64.., [64,128) = gate bias of the matching columns
+          const int o = (lane < 16) ? (half * 64 + lane * 4) : (128 + half * 64 + (lane - 16) * 4);
+          bv = __ldg(reinterpret_cast<const float4*>(bsrc + o));
+        } else {
+          bv = __ldg(reinterpret_cast<const float4*>(bsrc + half * 128 + lane * 4));
+        }
+        reinterpret_cast<float4*>(bias_s)[lane] = bv;
       }
-      ptx::mbar_wait(&tmem_full[acc], acc_phase);
-      ptx::tc_fence_after();
-      __syncwarp();
-      const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(quad * 32) << 16);
 
-      // global row of (row-in-warp r): 2-D: m_blk*128 + quad*32 + r ; conv: contiguous rows of (b, t2, f2)
-      long long warp_row0;
-      int rows_valid;          // rows of this warp's 32 that exist
-      bool row_live = true;    // thread's own row (thread = row layout), conv time mask
+      long long warp_row0;     // global output row of row 0 of this warp's 32
+      int rows_valid;          // how many of the 32 rows exist
+      bool row_live = true;    // conv: thread's own row lies inside the utterance's valid length
       if constexpr (AMODE == A_2D) {
         warp_row0 = static_cast<long long>(m_blk) * 128 + quad * 32;
         const long long rem = static_cast<long long>(p.M) - warp_row0;
@@ -187,10 +191,41 @@ gemm2_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         row_live = blk_ok && (t0 + (lane >> 4)) < p.conv_len2[b];
       }
 
+      [[maybe_unused]] float4 rr[2][8];
+      [[maybe_unused]] const int c4 = (lane & 7) * 4;
+      if constexpr (EPI == EPI_BIAS_RES_F32) {
+        // first chunk's residual goes out before we even wait for the accumulator
+        const size_t col = static_cast<size_t>(n_blk) * BN + half * 128 + c4;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = i * 4 + (lane >> 3);
+          rr[0][i] = r < rows_valid ? *reinterpret_cast<const float4*>(p.res + static_cast<size_t>(warp_row0 + r) * p.ldo + col)
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+
+      ptx::mbar_wait(&tmem_full[acc], acc_phase);
+      ptx::tc_fence_after();
+      __syncwarp();
+      const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(quad * 32) << 16);
+
       if constexpr (EPI == EPI_BIAS_RES_F32 || EPI == EPI_BIAS_F32) {
         float* outp = reinterpret_cast<float*>(p.out);
-#pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci) {
+          const int c = half * 128 + ci * 32;
+          const size_t col = static_cast<size_t>(n_blk) * BN + c + c4;
+          if constexpr (EPI == EPI_BIAS_RES_F32) {
+            if (ci + 1 < 4) {   // residual of the next chunk in flight while this one is transposed and stored
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int r = i * 4 + (lane >> 3);
+                rr[(ci + 1) & 1][i] = r < rows_valid
+                                          ? *reinterpret_cast<const float4*>(p.res + static_cast<size_t>(warp_row0 + r) * p.ldo + col + 32)
+                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+            }
+          }
           uint32_t v[32];
           ptx::tmem_ld_32x32b_x32(taddr + c, v);
           ptx::tmem_ld_wait();
@@ -200,21 +235,19 @@ gemm2_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             srow[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
                                   __uint_as_float(v[4 * q + 3]));
           __syncwarp();
-          const int c4 = (lane & 7) * 4;
-          const float4 bv = *reinterpret_cast<const float4*>(bias_s + c + c4);
+          const float4 bv = *reinterpret_cast<const float4*>(bias_s + ci * 32 + c4);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int r = i * 4 + (lane >> 3);
             if (r < rows_valid) {
               float4 a = *reinterpret_cast<const float4*>(stg + r * 36 + c4);
-              const size_t off = static_cast<size_t>(warp_row0 + r) * p.ldo + n_blk * BN + c + c4;
               a.x += bv.x; a.y += bv.y; a.z += bv.z; a.w += bv.w;
               if constexpr (EPI == EPI_BIAS_RES_F32) {
-                const float4 rr = *reinterpret_cast<const float4*>(p.res + off);
-                a.x = fmaf(p.scale, a.x, rr.x); a.y = fmaf(p.scale, a.y, rr.y);
-                a.z = fmaf(p.scale, a.z, rr.z); a.w = fmaf(p.scale, a.w, rr.w);
+                const float4 x = rr[ci & 1][i];
+                a.x = fmaf(p.scale, a.x, x.x); a.y = fmaf(p.scale, a.y, x.y);
+                a.z = fmaf(p.scale, a.z, x.z); a.w = fmaf(p.scale, a.w, x.w);
               }
-              *reinterpret_cast<float4*>(outp + off) = a;
+              *reinterpret_cast<float4*>(outp + static_cast<size_t>(warp_row0 + r) * p.ldo + col) = a;
             }
           }
           __syncwarp();
@@ -223,7 +256,8 @@ gemm2_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         __half* outp = reinterpret_cast<__half*>(p.out);
         uint32_t* stw = reinterpret_cast<uint32_t*>(stg);
 #pragma unroll 1
-        for (int c = 0; c < 128; c += 32) {
+        for (int ci = 0; ci < 2; ++ci) {
+          const int c = half * 64 + ci * 32;   // value columns c.., gate columns 128 + c..
           uint32_t va[32], vb[32];
           ptx::tmem_ld_32x32b_x32(taddr + c, va);
           ptx::tmem_ld_32x32b_x32(taddr + 128 + c, vb);
@@ -231,8 +265,8 @@ gemm2_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           uint32_t pk[16];
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            const float4 ba = *reinterpret_cast<const float4*>(bias_s + c + j);
-            const float4 bb = *reinterpret_cast<const float4*>(bias_s + 128 + c + j);
+            const float4 ba = *reinterpret_cast<const float4*>(bias_s + ci * 32 + j);
+            const float4 bb = *reinterpret_cast<const float4*>(bias_s + 64 + ci * 32 + j);
             const float g0 = (__uint_as_float(va[j]) + ba.x) * sigmoid_f(__uint_as_float(vb[j]) + bb.x);
             const float g1 = (__uint_as_float(va[j + 1]) + ba.y) * sigmoid_f(__uint_as_float(vb[j + 1]) + bb.y);
             const float g2 = (__uint_as_float(va[j + 2]) + ba.z) * sigmoid_f(__uint_as_float(vb[j + 2]) + bb.z);
@@ -259,7 +293,8 @@ gemm2_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         __half* outp = reinterpret_cast<__half*>(p.out);
         uint32_t* stw = reinterpret_cast<uint32_t*>(stg);
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 64) {
+        for (int ci = 0; ci < 2; ++ci) {
+          const int c = half * 128 + ci * 64;
           uint32_t v[64];
           ptx::tmem_ld_32x32b_x32(taddr + c, v);
           ptx::tmem_ld_32x32b_x32(taddr + c + 32, v + 32);
@@ -267,7 +302,7 @@ gemm2_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           uint32_t pk[32];
 #pragma unroll
           for (int j = 0; j < 64; j += 4) {
-            const float4 bv = *reinterpret_cast<const float4*>(bias_s + c + j);
+            const float4 bv = *reinterpret_cast<const float4*>(bias_s + ci * 64 + j);
             float x0 = __uint_as_float(v[j]) + bv.x, x1 = __uint_as_float(v[j + 1]) + bv.y;
             float x2 = __uint_as_float(v[j + 2]) + bv.z, x3 = __uint_as_float(v[j + 3]) + bv.w;
             if constexpr (EPI == EPI_BIAS_SILU_F16) { x0 = silu_f(x0); x1 = silu_f(x1); x2 = silu_f(x2); x3 = silu_f(x3); }

@@ -160,9 +160,9 @@ __global__ void __launch_bounds__(256) ln_out_ln_kernel(const float* __restrict_
 // g: [B, T, 768] fp16 (GLU output, NOT yet pad-masked: masked here on load, gigaam/encoder.py:400-401)
 // w: [768, KW] fp32, b: [768] fp32 with eval BatchNorm folded in.  out = silu(conv) fp16.
 // block = (channel tile of 128, time tile of 64, b); thread = 2 channels x 16 time steps.
-constexpr int kDwTT = 64;
-constexpr int kDwCT = 128;
-constexpr int kDwPerThread = 16;
+constexpr int kDwTT = 32;          // time steps per block
+constexpr int kDwCT = 128;         // channels per block
+constexpr int kDwPerThread = 8;    // consecutive outputs per thread (x 2 channels)
 
 template <int KW>
 __global__ void __launch_bounds__(256) dwconv_bn_silu_kernel(const __half* __restrict__ g, const float* __restrict__ w,
@@ -170,44 +170,44 @@ __global__ void __launch_bounds__(256) dwconv_bn_silu_kernel(const __half* __res
                                                              __half* __restrict__ out, int T) {
   constexpr int kHalo = (KW - 1) / 2;
   constexpr int kRows = kDwTT + KW - 1;
-  __shared__ __half2 tile[kRows][kDwCT / 2];
+  __shared__ __align__(16) __half2 tile[kRows][kDwCT / 2];
+  __shared__ float2 w_s[KW][kDwCT / 2];          // taps transposed: w_s[k][channel pair]
   const int c0 = blockIdx.x * kDwCT;
   const int t0 = blockIdx.y * kDwTT;
   const int b = blockIdx.z;
   const int L = min(len[b], T);
   const __half* gb = g + static_cast<size_t>(b) * T * kD;
-  for (int i = threadIdx.x; i < kRows * (kDwCT / 2); i += blockDim.x) {
-    const int rr = i / (kDwCT / 2), cc = i % (kDwCT / 2);
+  // input tile: 16-byte loads, one 256-byte row segment per 16 threads; padded frames / halo -> 0
+  for (int i = threadIdx.x; i < kRows * (kDwCT / 8); i += blockDim.x) {
+    const int rr = i / (kDwCT / 8), c8 = i % (kDwCT / 8);
     const int t = t0 + rr - kHalo;
-    __half2 v = __floats2half2_rn(0.f, 0.f);
-    if (t >= 0 && t < L) v = *reinterpret_cast<const __half2*>(gb + static_cast<size_t>(t) * kD + c0 + 2 * cc);
-    tile[rr][cc] = v;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (t >= 0 && t < L) v = *reinterpret_cast<const uint4*>(gb + static_cast<size_t>(t) * kD + c0 + 8 * c8);
+    *reinterpret_cast<uint4*>(&tile[rr][4 * c8]) = v;
+  }
+  for (int i = threadIdx.x; i < KW * kDwCT; i += blockDim.x) {
+    const int c = i / KW, k = i % KW;            // coalesced read of w[c0 + c][k]
+    reinterpret_cast<float*>(&w_s[k][c >> 1])[c & 1] = __ldg(w + static_cast<size_t>(c0 + c) * KW + k);
   }
   __syncthreads();
   const int cp = threadIdx.x % (kDwCT / 2);      // channel pair
   const int tg = threadIdx.x / (kDwCT / 2);      // time group (0..3)
   const int ch = c0 + 2 * cp;
-  float w0[KW], w1[KW];
+  const int rbase = tg * kDwPerThread;
+  float2 x[kDwPerThread + KW - 1];
 #pragma unroll
-  for (int k = 0; k < KW; ++k) {
-    w0[k] = __ldg(w + static_cast<size_t>(ch) * KW + k);
-    w1[k] = __ldg(w + static_cast<size_t>(ch + 1) * KW + k);
-  }
+  for (int j = 0; j < kDwPerThread + KW - 1; ++j) x[j] = __half22float2(tile[rbase + j][cp]);
   float a0[kDwPerThread], a1[kDwPerThread];
   const float bb0 = __ldg(bias + ch), bb1 = __ldg(bias + ch + 1);
 #pragma unroll
   for (int o = 0; o < kDwPerThread; ++o) { a0[o] = bb0; a1[o] = bb1; }
-  const int rbase = tg * kDwPerThread;
 #pragma unroll
-  for (int j = 0; j < kDwPerThread + KW - 1; ++j) {
-    const float2 x = __half22float2(tile[rbase + j][cp]);
+  for (int k = 0; k < KW; ++k) {
+    const float2 wk = w_s[k][cp];
 #pragma unroll
     for (int o = 0; o < kDwPerThread; ++o) {
-      const int k = j - o;
-      if (k >= 0 && k < KW) {
-        a0[o] = fmaf(w0[k], x.x, a0[o]);
-        a1[o] = fmaf(w1[k], x.y, a1[o]);
-      }
+      a0[o] = fmaf(wk.x, x[o + k].x, a0[o]);
+      a1[o] = fmaf(wk.y, x[o + k].y, a1[o]);
     }
   }
   __half* ob = out + static_cast<size_t>(b) * T * kD;
