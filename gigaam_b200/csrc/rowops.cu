@@ -100,22 +100,22 @@ __global__ void __launch_bounds__(256) ln_rope_f16_kernel(const float* __restric
   const int t = row % T;
   const float* cs = rope_cos + static_cast<size_t>(t) * half_dim;
   const float* sn = rope_sin + static_cast<size_t>(t) * half_dim;
-  const int hd = 2 * half_dim;
+  // head_dim and half_dim are multiples of 4, so a float4 never straddles the rotation boundary: the partner of
+  // a float4 is the float4 half_dim/4 positions away (conflict-free 16-byte smem reads, aligned table reads)
+  const int hq = half_dim >> 2;            // float4 per half head
   uint2* orr = reinterpret_cast<uint2*>(out_r + static_cast<size_t>(row) * kD);
 #pragma unroll
   for (int i = 0; i < kVec; ++i) {
-    const int e0 = (lane + 32 * i) * 4;
-    float r[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int e = e0 + j;
-      const int d = e % hd;
-      const int f = d < half_dim ? d : d - half_dim;
-      const float a = srow[w][e];
-      const float p = d < half_dim ? -srow[w][e + half_dim] : srow[w][e - half_dim];
-      r[j] = a * cs[f] + p * sn[f];
-    }
-    orr[lane + 32 * i] = pack4(make_float4(r[0], r[1], r[2], r[3]));
+    const int f4 = lane + 32 * i;          // float4 index in the row
+    const int q = f4 % (2 * hq);           // position inside the head
+    const bool lo = q < hq;
+    const float4 a = s4[f4];
+    const float4 pt = s4[lo ? f4 + hq : f4 - hq];
+    const float sg = lo ? -1.f : 1.f;
+    const float4 c = __ldg(reinterpret_cast<const float4*>(cs) + (lo ? q : q - hq));
+    const float4 s = __ldg(reinterpret_cast<const float4*>(sn) + (lo ? q : q - hq));
+    orr[f4] = pack4(make_float4(fmaf(sg * pt.x, s.x, a.x * c.x), fmaf(sg * pt.y, s.y, a.y * c.y),
+                                fmaf(sg * pt.z, s.z, a.z * c.z), fmaf(sg * pt.w, s.w, a.w * c.w)));
   }
 }
 
@@ -171,7 +171,6 @@ __global__ void __launch_bounds__(256) dwconv_bn_silu_kernel(const __half* __res
   constexpr int kHalo = (KW - 1) / 2;
   constexpr int kRows = kDwTT + KW - 1;
   __shared__ __align__(16) __half2 tile[kRows][kDwCT / 2];
-  __shared__ float2 w_s[KW][kDwCT / 2];          // taps transposed: w_s[k][channel pair]
   const int c0 = blockIdx.x * kDwCT;
   const int t0 = blockIdx.y * kDwTT;
   const int b = blockIdx.z;
@@ -185,10 +184,6 @@ __global__ void __launch_bounds__(256) dwconv_bn_silu_kernel(const __half* __res
     if (t >= 0 && t < L) v = *reinterpret_cast<const uint4*>(gb + static_cast<size_t>(t) * kD + c0 + 8 * c8);
     *reinterpret_cast<uint4*>(&tile[rr][4 * c8]) = v;
   }
-  for (int i = threadIdx.x; i < KW * kDwCT; i += blockDim.x) {
-    const int c = i / KW, k = i % KW;            // coalesced read of w[c0 + c][k]
-    reinterpret_cast<float*>(&w_s[k][c >> 1])[c & 1] = __ldg(w + static_cast<size_t>(c0 + c) * KW + k);
-  }
   __syncthreads();
   const int cp = threadIdx.x % (kDwCT / 2);      // channel pair
   const int tg = threadIdx.x / (kDwCT / 2);      // time group (0..3)
@@ -198,12 +193,14 @@ __global__ void __launch_bounds__(256) dwconv_bn_silu_kernel(const __half* __res
 #pragma unroll
   for (int j = 0; j < kDwPerThread + KW - 1; ++j) x[j] = __half22float2(tile[rbase + j][cp]);
   float a0[kDwPerThread], a1[kDwPerThread];
-  const float bb0 = __ldg(bias + ch), bb1 = __ldg(bias + ch + 1);
+  const float2 bb = __ldg(reinterpret_cast<const float2*>(bias + ch));
 #pragma unroll
-  for (int o = 0; o < kDwPerThread; ++o) { a0[o] = bb0; a1[o] = bb1; }
+  for (int o = 0; o < kDwPerThread; ++o) { a0[o] = bb.x; a1[o] = bb.y; }
+  // taps are stored transposed [KW][768]: one coalesced 8-byte load per tap, L1-resident across the block
+  const float2* wt = reinterpret_cast<const float2*>(w + ch);
 #pragma unroll
   for (int k = 0; k < KW; ++k) {
-    const float2 wk = w_s[k][cp];
+    const float2 wk = __ldg(wt + static_cast<size_t>(k) * (kD / 2));
 #pragma unroll
     for (int o = 0; o < kDwPerThread; ++o) {
       a0[o] = fmaf(wk.x, x[o + k].x, a0[o]);
@@ -215,9 +212,12 @@ __global__ void __launch_bounds__(256) dwconv_bn_silu_kernel(const __half* __res
   for (int o = 0; o < kDwPerThread; ++o) {
     const int t = t0 + rbase + o;
     if (t < T) {
-      const float y0 = a0[o] / (1.f + __expf(-a0[o]));
-      const float y1 = a1[o] / (1.f + __expf(-a1[o]));
-      *reinterpret_cast<__half2*>(ob + static_cast<size_t>(t) * kD + ch) = __floats2half2_rn(y0, y1);
+      // silu(a) = 0.5 a (1 + tanh(0.5 a)): one MUFU, no division
+      const float h0 = 0.5f * a0[o], h1 = 0.5f * a1[o];
+      float t0v, t1v;
+      asm("tanh.approx.f32 %0, %1;" : "=f"(t0v) : "f"(h0));
+      asm("tanh.approx.f32 %0, %1;" : "=f"(t1v) : "f"(h1));
+      *reinterpret_cast<__half2*>(ob + static_cast<size_t>(t) * kD + ch) = __floats2half2_rn(fmaf(h0, t0v, h0), fmaf(h1, t1v, h1));
     }
   }
 }
@@ -245,8 +245,9 @@ __global__ void __launch_bounds__(256) dwconv_ln_silu_kernel(const __half* __res
 #pragma unroll
     for (int i = 0; i < 12; ++i) {
       const float2 x = __half22float2(src[i]);
-      acc[2 * i] = fmaf(__ldg(w + static_cast<size_t>(lane * 24 + 2 * i) * KW + k), x.x, acc[2 * i]);
-      acc[2 * i + 1] = fmaf(__ldg(w + static_cast<size_t>(lane * 24 + 2 * i + 1) * KW + k), x.y, acc[2 * i + 1]);
+      const float2 wk = __ldg(reinterpret_cast<const float2*>(w + static_cast<size_t>(k) * kD + lane * 24 + 2 * i));
+      acc[2 * i] = fmaf(wk.x, x.x, acc[2 * i]);
+      acc[2 * i + 1] = fmaf(wk.y, x.y, acc[2 * i + 1]);
     }
   }
   float s = 0.f;

@@ -187,7 +187,7 @@ class Engine:
             lw.cn_g, lw.cn_b = None, None
         else:
             lw.cn_g, lw.cn_b = self._dev(f("conv.batch_norm.weight")), self._dev(f("conv.batch_norm.bias"))
-        lw.dw_w, lw.dw_b = self._dev(dw), self._dev(db)
+        lw.dw_w, lw.dw_b = self._dev(dw.t()), self._dev(db)     # taps transposed to [k, d]: coalesced per-tap loads
         lw.pw2_w = self._dev(f("conv.pointwise_conv2.weight").reshape(d, d), h16)
         lw.pw2_b = self._dev(f("conv.pointwise_conv2.bias"))
         lw.ln_ff2_g, lw.ln_ff2_b = self._dev(f("norm_feed_forward2.weight")), self._dev(f("norm_feed_forward2.bias"))

@@ -62,7 +62,7 @@ typedef struct gam_layer_weights {
   const float *ln_conv_g, *ln_conv_b;
   const void* pw1_w; /* h [2d, d], rows permuted so every 256-row tile is [128 value | 128 gate] */
   const float* pw1_b; /* f [2d], same permutation */
-  const float* dw_w;  /* f [d, k]  (eval BatchNorm folded in when conv_norm == 0) */
+  const float* dw_w;  /* f [k, d]  depthwise taps, tap-major (eval BatchNorm folded in when conv_norm == 0) */
   const float* dw_b;  /* f [d] */
   const float *cn_g, *cn_b; /* conv LayerNorm affine (conv_norm == 1), else NULL */
   const void* pw2_w;  /* h [d, d] */
