@@ -425,9 +425,244 @@ __global__ void __launch_bounds__(64 + kResMaxQT * 128) attention_resident_kerne
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Persistent variant for T <= 256 (the headline config, T' = 251): one CTA per SM loops over (utterance, head)
+// work items.  Q/K/V of item i+1 stream into the other half of a double-buffered smem ring while item i is in
+// its softmax, P never touches shared memory (softmax warps write it as packed fp16 straight over the consumed
+// part of their S rows in TMEM with tcgen05.st, and P.V runs as a TS-mode tcgen05.mma with A in TMEM), and O
+// lands in the dead upper half of the tile's S region.  TMEM: 2 query tiles x 256 columns.
+struct AttnPersParams {
+  int T, nkb, B, H;
+  const int* klen;
+  __half* out;
+  int ld_out, dk;
+  float scale_log2;
+};
+
+__global__ void __launch_bounds__(64 + 256, 1) attention_persistent_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
+                                                                          const AttnPersParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int nkb = p.nkb;                    // 1 or 2: key blocks == query tiles
+  const int item_bytes = 3 * nkb * kTileBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * item_bytes);
+  uint64_t* kv_full = bars;        // [2] ring buffers
+  uint64_t* kv_empty = bars + 2;   // [2]
+  uint64_t* s_full = bars + 4;     // [2] query tiles
+  uint64_t* p_full = bars + 6;     // [2]
+  uint64_t* o_full = bars + 8;     // [2]
+  uint64_t* o_empty = bars + 10;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int n_items = p.B * p.H;
+  const int dmodel = p.ld_out;
+
+  if (warp_idx == 0 && ptx::elect_one()) {
+    ptx::prefetch_tmap(&tmap_qkv);
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&kv_full[i], 1);
+      ptx::mbar_init(&kv_empty[i], 1);
+      ptx::mbar_init(&s_full[i], 1);
+      ptx::mbar_init(&p_full[i], 4);
+      ptx::mbar_init(&o_full[i], 1);
+      ptx::mbar_init(&o_empty[i], 4);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp_idx == 1) ptx::tmem_alloc<512>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp_idx == 0) {
+    // ===================================================== TMA producer
+    if (ptx::elect_one()) {
+      int it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const uint32_t par = (it >> 1) & 1;
+        const int b = item / p.H, h = item % p.H;
+        const int row0 = b * p.T;
+        uint8_t* sQ = smem + buf * item_bytes;
+        uint8_t* sK = sQ + nkb * kTileBytes;
+        uint8_t* sV = sK + nkb * kTileBytes;
+        ptx::mbar_wait(&kv_empty[buf], par ^ 1);
+        ptx::mbar_arrive_expect_tx(&kv_full[buf], item_bytes);
+        for (int t = 0; t < nkb; ++t) {
+          ptx::tma_load_2d(sQ + t * kTileBytes, &tmap_qkv, &kv_full[buf], h * p.dk, row0 + t * 128);
+          ptx::tma_load_2d(sK + t * kTileBytes, &tmap_qkv, &kv_full[buf], dmodel + h * p.dk, row0 + t * 128);
+          ptx::tma_load_2d(sV + t * kTileBytes, &tmap_qkv, &kv_full[buf], 2 * dmodel + h * p.dk, row0 + t * 128);
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ===================================================== MMA issuer
+    constexpr uint32_t kIdescS = ptx::make_idesc_f16(128, 128, 0, 0);
+    constexpr uint32_t kIdescPV = ptx::make_idesc_f16(128, 64, 0, 1);   // B (= V) MN-major; A (= P) from TMEM
+    const int ksteps_qk = p.dk / 16;
+    int it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const uint32_t ipar = it & 1;
+      uint8_t* sQ = smem + buf * item_bytes;
+      uint8_t* sK = sQ + nkb * kTileBytes;
+      uint8_t* sV = sK + nkb * kTileBytes;
+      ptx::mbar_wait(&kv_full[buf], (it >> 1) & 1);
+      for (int qt = 0; qt < nkb; ++qt) {
+        ptx::mbar_wait(&o_empty[qt], ipar ^ 1);   // previous item's O has been read out of this tile's region
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          const uint32_t qa = ptx::smem_u32(sQ + qt * kTileBytes);
+          for (int kb = 0; kb < nkb; ++kb) {
+            const uint32_t ka = ptx::smem_u32(sK + kb * kTileBytes);
+            for (int k = 0; k < ksteps_qk; ++k)
+              ptx::mma_f16_ss(tmem_base + qt * 256 + kb * 128, ptx::make_smem_desc_sw128(qa + k * 32, 16, 1024),
+                              ptx::make_smem_desc_sw128(ka + k * 32, 16, 1024), kIdescS, k != 0 ? 1u : 0u);
+          }
+          ptx::mma_commit(&s_full[qt]);
+        }
+        __syncwarp();
+      }
+      for (int qt = 0; qt < nkb; ++qt) {
+        ptx::mbar_wait(&p_full[qt], ipar);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          for (int kb = 0; kb < nkb; ++kb) {
+            const uint32_t va = ptx::smem_u32(sV + kb * kTileBytes);
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks)
+              ptx::mma_f16_ts(tmem_base + qt * 256 + 128, tmem_base + qt * 256 + (kb * 8 + ks) * 8,
+                              ptx::make_smem_desc_sw128(va + ks * 2048, 1024, 1024), kIdescPV, (kb | ks) != 0 ? 1u : 0u);
+          }
+          ptx::mma_commit(&o_full[qt]);
+          if (qt == nkb - 1) ptx::mma_commit(&kv_empty[buf]);   // every MMA that reads this ring slot has retired
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp_idx < 2 + 4 * nkb) {
+    // ===================================================== softmax + output (one warpgroup per query tile)
+    const int qt = (warp_idx - 2) >> 2;
+    const int quad = warp_idx & 3;
+    const int lane = threadIdx.x & 31;
+    const int r = quad * 32 + lane;
+    const uint32_t t_s = tmem_base + qt * 256 + (static_cast<uint32_t>(quad * 32) << 16);
+    int it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      const uint32_t ipar = it & 1;
+      const int b = item / p.H, h = item % p.H;
+      int klen = p.T;
+      if (p.klen != nullptr) klen = min(max(p.klen[b], 0), p.T);
+      const int nchunks = (klen + 31) >> 5;
+      ptx::mbar_wait(&s_full[qt], ipar);
+      ptx::tc_fence_after();
+      float m = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < nchunks; ++c) {
+        uint32_t v[32];
+        ptx::tmem_ld_32x32b_x32(t_s + c * 32, v);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (c * 32 + j < klen) m = fmaxf(m, __uint_as_float(v[j]));
+      }
+      if (m == -INFINITY) m = 0.f;
+      const float mc = m * p.scale_log2;
+      float sum = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < nkb * 4; ++c) {
+        uint32_t pk[16];
+        if (c < nchunks) {
+          uint32_t v[32];
+          ptx::tmem_ld_32x32b_x32(t_s + c * 32, v);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const float p0 = (c * 32 + j < klen) ? ex2(fmaf(__uint_as_float(v[j]), p.scale_log2, -mc)) : 0.f;
+            const float p1 = (c * 32 + j + 1 < klen) ? ex2(fmaf(__uint_as_float(v[j + 1]), p.scale_log2, -mc)) : 0.f;
+            sum += p0 + p1;
+            __half2 hh = __floats2half2_rn(p0, p1);
+            pk[j >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) pk[j] = 0u;
+        }
+        // P chunk c (32 keys = 16 packed columns) overwrites columns [16c, 16c+16) of this row: part of S chunk c/2,
+        // already consumed
+        ptx::tmem_st_32x32b_x16(t_s + c * 16, pk);
+      }
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&p_full[qt]);
+      ptx::mbar_wait(&o_full[qt], ipar);
+      ptx::tc_fence_after();
+      uint32_t ov[48];
+      ptx::tmem_ld_32x32b_x16(t_s + 128, ov);
+      ptx::tmem_ld_32x32b_x16(t_s + 144, ov + 16);
+      ptx::tmem_ld_32x32b_x16(t_s + 160, ov + 32);
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&o_empty[qt]);   // region free for the next item's S
+      const float inv = sum > 0.f ? 1.0f / sum : 0.f;
+      const int q = qt * 128 + r;
+      if (q < p.T) {
+        __half* dst = p.out + (static_cast<size_t>(b) * p.T + q) * p.ld_out + h * p.dk;
+#pragma unroll
+        for (int c = 0; c < 48; c += 8) {
+          if (c < p.dk) {
+            uint32_t o[4];
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) {
+              __half2 hh = __floats2half2_rn(__uint_as_float(ov[c + j]) * inv, __uint_as_float(ov[c + j + 1]) * inv);
+              o[j >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+            }
+            *reinterpret_cast<uint4*>(dst + c) = make_uint4(o[0], o[1], o[2], o[3]);
+          }
+        }
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<512>(tmem_base);
+  }
+}
+
 }  // namespace
 
 int attention_smem_bytes(int nkb) { return (3 + 2 * nkb) * kTileBytes + 128 + 1024; }
+
+static int launch_attention_persistent(const CUtensorMap* tmap_qkv, const int* klen, __half* out, int B, int T, int H, int dk,
+                                       int d_model, int num_sms, cudaStream_t s) {
+  AttnPersParams p;
+  p.T = T;
+  p.nkb = (T + 127) / 128;
+  p.B = B;
+  p.H = H;
+  p.klen = klen;
+  p.out = out;
+  p.ld_out = d_model;
+  p.dk = dk;
+  p.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(dk));
+  static int attr_set = 0;
+  if (!attr_set) {
+    cudaFuncSetAttribute(attention_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_set = 1;
+  }
+  const int items = B * H;
+  const int grid = items < num_sms ? items : num_sms;
+  const int smem = 2 * 3 * p.nkb * kTileBytes + 256 + 1024;
+  attention_persistent_kernel<<<grid, 64 + 128 * p.nkb, smem, s>>>(*tmap_qkv, p);
+  return 0;
+}
 static int attention_res_smem_bytes(int nkb, int QT) { return (QT + 2 * nkb + QT * 2 * nkb) * kTileBytes + 128 + 1024; }
 
 static int launch_attention_resident(const CUtensorMap* tmap_qkv, const int* klen, __half* out, int B, int T, int H, int dk,
@@ -462,6 +697,16 @@ int launch_attention(const CUtensorMap* tmap_qkv, const int* klen, __half* out, 
     const char* e = getenv("GAM_ATTN_V1");
     force_v1 = (e && e[0] == '1') ? 1 : 0;
   }
+  static int force_v2 = -1, num_sms = 0;
+  if (force_v2 < 0) {
+    const char* e = getenv("GAM_ATTN_V2");
+    force_v2 = (e && e[0] == '1') ? 1 : 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  if (nkb <= 2 && !force_v1 && !force_v2)
+    return launch_attention_persistent(tmap_qkv, klen, out, B, T, H, dk, d_model, num_sms, s);
   if (nkb <= kResMaxKB && !force_v1) return launch_attention_resident(tmap_qkv, klen, out, B, T, H, dk, d_model, s);
   AttnParams p;
   p.T = T;
