@@ -36,7 +36,7 @@ class GamLayerWeights(C.Structure):
 WEIGHT_FIELDS_HEAD = ("window", "dft_cos", "dft_sin", "mel_fb", "sub1_w", "sub1_b", "sub2_w", "sub2_b",
                       "sub_out_w", "sub_out_b", "rope_cos", "rope_sin")
 WEIGHT_FIELDS_TAIL = ("ctc_w", "ctc_b", "rnnt_enc_w", "rnnt_enc_b", "rnnt_emb_gates", "rnnt_whh_t", "rnnt_wp_t",
-                      "rnnt_bp", "rnnt_wo", "rnnt_bo")
+                      "rnnt_bp", "rnnt_wo", "rnnt_bo", "c1d_w1", "c1d_b1", "c1d_w2", "c1d_b2")
 
 
 class GamWeights(C.Structure):

@@ -189,7 +189,32 @@ __global__ void __launch_bounds__(256) subsample_conv1_kernel(const float* __res
   }
 }
 
+// mel [B, F, M] f32 -> [B, M, F] f16, frames t >= len0[b] zeroed (the _mask_time before the first conv1d,
+// gigaam/encoder.py:118).  32 x 32 smem transpose tiles.
+__global__ void __launch_bounds__(256) mel_to_tmajor_f16_kernel(const float* __restrict__ mel, const int* __restrict__ len0,
+                                                                __half* __restrict__ out, int F, int M) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int t0 = blockIdx.x * 32, f0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 8 rows per pass
+  const int L = len0[b];
+  for (int i = ty; i < 32; i += 8) {
+    const int f = f0 + i, t = t0 + tx;
+    tile[i][tx] = (f < F && t < M && t < L) ? mel[(static_cast<size_t>(b) * F + f) * M + t] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int t = t0 + i, f = f0 + tx;
+    if (t < M && f < F) out[(static_cast<size_t>(b) * M + t) * F + f] = __float2half_rn(tile[tx][i]);
+  }
+}
+
 }  // namespace
+
+void launch_mel_to_tmajor_f16(const float* mel, const int* len0, __half* out, int B, int F, int M, cudaStream_t s) {
+  dim3 grid((M + 31) / 32, (F + 31) / 32, B);
+  mel_to_tmajor_f16_kernel<<<grid, 256, 0, s>>>(mel, len0, out, F, M);
+}
 
 int logmel_smem_bytes(int n_fft) {
   const int K = n_fft / 2 + 1, KP = K | 1;

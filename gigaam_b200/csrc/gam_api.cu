@@ -57,6 +57,20 @@ static int make_tmap_conv4d(CUtensorMap* m, const void* base, uint64_t B, uint64
   return r == CUDA_SUCCESS ? 0 : -static_cast<int>(r) - 1000;
 }
 
+// 3-D time-major activation [B, T, C] fp16 for the stride-2 conv1d: box = 128 output frames (256 input frames
+// traversed with stride 2) x 64 channels
+static int make_tmap_conv3d(CUtensorMap* m, const void* base, uint64_t B, uint64_t T, uint64_t C) {
+  if (init_encode() != 0) return -1;
+  cuuint64_t dims[3] = {C, T, B};
+  cuuint64_t strides[2] = {C * 2, T * C * 2};
+  cuuint32_t box[3] = {64, 256, 1};
+  cuuint32_t estr[3] = {1, 2, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -static_cast<int>(r) - 1000;
+}
+
 static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 
 struct LayerMaps {
@@ -72,6 +86,8 @@ struct Plan {
   // workspace carve-up
   int *len0 = nullptr, *len1 = nullptr, *len2 = nullptr;
   __half *s1 = nullptr, *s2 = nullptr, *a16 = nullptr, *r16 = nullptr, *big16 = nullptr, *o16 = nullptr, *g16 = nullptr;
+  __half* melT = nullptr;   // conv1d subsampling: time-major fp16 copy of the log-mel
+  CUtensorMap m_melT, m_s1_3d;
   float* x = nullptr;
   int64_t bytes = 0;
   CUtensorMap m_s1, m_s2, m_a16, m_r16, m_hid, m_qkv, m_o16;
@@ -151,8 +167,8 @@ void plan_geometry(const gam_handle* h, int B, int64_t M, Plan* p) {
   p->M = M;
   p->T1 = sub_out_len(static_cast<int>(M), k, pad);
   p->T2 = sub_out_len(p->T1, k, pad);
-  p->F1 = sub_out_len(c.feat_in, k, pad);
-  p->F2 = sub_out_len(p->F1, k, pad);
+  p->F1 = c.subsampling == 0 ? sub_out_len(c.feat_in, k, pad) : 1;
+  p->F2 = c.subsampling == 0 ? sub_out_len(p->F1, k, pad) : 1;
   p->R = B * p->T2;
 }
 
@@ -178,6 +194,7 @@ int64_t plan_carve(const gam_handle* h, Plan* p, uint8_t* base) {
   p->g16 = reinterpret_cast<__half*>(take(R * d * 2));
   p->s2 = reinterpret_cast<__half*>(take(R * static_cast<int64_t>(p->F2) * d * 2));
   p->s1 = reinterpret_cast<__half*>(take(B * static_cast<int64_t>(p->T1) * p->F1 * d * 2));
+  p->melT = reinterpret_cast<__half*>(take(c.subsampling == 1 ? B * p->M * static_cast<int64_t>(c.feat_in) * 2 : 0));
   return off;
 }
 
@@ -204,8 +221,13 @@ Plan* get_plan(gam_handle* h, int B, int64_t M, void* ws, int64_t ws_bytes) {
   const gam_config& c = h->cfg;
   const uint64_t d = c.d_model, R = p->R;
   int rc = 0;
-  rc |= make_tmap_conv4d(&p->m_s1, p->s1, B, p->T1, p->F1, d);
-  rc |= make_tmap_2d_f16(&p->m_s2, p->s2, R, static_cast<uint64_t>(p->F2) * d, static_cast<uint64_t>(p->F2) * d, 128, 64);
+  if (c.subsampling == 0) {
+    rc |= make_tmap_conv4d(&p->m_s1, p->s1, B, p->T1, p->F1, d);
+    rc |= make_tmap_2d_f16(&p->m_s2, p->s2, R, static_cast<uint64_t>(p->F2) * d, static_cast<uint64_t>(p->F2) * d, 128, 64);
+  } else {
+    rc |= make_tmap_conv3d(&p->m_melT, p->melT, B, static_cast<uint64_t>(p->M), c.feat_in);
+    rc |= make_tmap_conv3d(&p->m_s1_3d, p->s1, B, p->T1, d);
+  }
   rc |= make_tmap_2d_f16(&p->m_a16, p->a16, R, d, d, 128, 64);
   rc |= make_tmap_2d_f16(&p->m_r16, p->r16, R, d, d, 128, 64);
   rc |= make_tmap_2d_f16(&p->m_hid, p->big16, R, c.d_ff, c.d_ff, 128, 64);
@@ -249,12 +271,14 @@ int gam_create(const gam_config* cfg, const gam_weights* w, int device, gam_hand
   h->device = device;
   *out = h;  // returned even on failure so the caller can read gam_last_error()
   const gam_config& c = h->cfg;
-  if (c.subsampling != 0) return fail(h, -10, "only conv2d subsampling is built in this round (got %d)", c.subsampling);
+  if (c.subsampling != 0 && c.subsampling != 1) return fail(h, -10, "unknown subsampling type %d", c.subsampling);
+  if (c.subsampling == 1 && (c.feat_in % 64 != 0 || (c.subs_kernel_size & 1) == 0))
+    return fail(h, -10, "conv1d subsampling needs feat_in %% 64 == 0 and an odd kernel size");
   if (c.self_attention != 0) return fail(h, -10, "only rotary self-attention is built in this round");
   if (c.d_model != 768 || c.d_model % c.n_heads != 0 || (c.d_model / c.n_heads) % 16 != 0)
     return fail(h, -10, "unsupported d_model/n_heads (%d/%d): kernels are specialised for d_model 768, d_k %% 16 == 0",
                 c.d_model, c.n_heads);
-  if (c.d_ff % 256 != 0 || c.subs_kernel_size != 3) return fail(h, -10, "unsupported d_ff / subs_kernel_size");
+  if (c.d_ff % 256 != 0 || (c.subsampling == 0 && c.subs_kernel_size != 3)) return fail(h, -10, "unsupported d_ff / subs_kernel_size");
   if (c.win_length != c.n_fft) return fail(h, -10, "win_length != n_fft is not supported");
   if (cudaSetDevice(device) != cudaSuccess) return fail(h, -11, "cudaSetDevice(%d) failed", device);
   cudaDeviceProp prop;
@@ -283,9 +307,15 @@ int gam_create(const gam_config* cfg, const gam_weights* w, int device, gam_hand
   }
   const int pad = (c.subs_kernel_size - 1) / 2;
   const int F1 = sub_out_len(c.feat_in, c.subs_kernel_size, pad), F2 = sub_out_len(F1, c.subs_kernel_size, pad);
-  if (F1 != 32 || F2 != 16) return fail(h, -10, "conv2d subsampling kernels are specialised for feat_in 64 (F1=32,F2=16)");
-  rc |= make_tmap_2d_f16(&h->m_sub2_w, w->sub2_w, d, 9 * d, 9 * d, 128, 64);
-  rc |= make_tmap_2d_f16(&h->m_sub_out_w, w->sub_out_w, d, static_cast<uint64_t>(F2) * d, static_cast<uint64_t>(F2) * d, 128, 64);
+  if (c.subsampling == 0) {
+    if (F1 != 32 || F2 != 16) return fail(h, -10, "conv2d subsampling kernels are specialised for feat_in 64 (F1=32,F2=16)");
+    rc |= make_tmap_2d_f16(&h->m_sub2_w, w->sub2_w, d, 9 * d, 9 * d, 128, 64);
+    rc |= make_tmap_2d_f16(&h->m_sub_out_w, w->sub_out_w, d, static_cast<uint64_t>(F2) * d, static_cast<uint64_t>(F2) * d, 128, 64);
+  } else {
+    const uint64_t k1 = static_cast<uint64_t>(c.subs_kernel_size) * c.feat_in, k2 = static_cast<uint64_t>(c.subs_kernel_size) * d;
+    rc |= make_tmap_2d_f16(&h->m_sub2_w, w->c1d_w1, d, k1, k1, 128, 64);        // stage 1: [d, taps * feat_in]
+    rc |= make_tmap_2d_f16(&h->m_sub_out_w, w->c1d_w2, d, k2, k2, 128, 64);     // stage 2: [d, taps * d]
+  }
   if (rc != 0) return fail(h, -2, "cuTensorMapEncodeTiled failed for weight maps (rc=%d)", rc);
   return 0;
 }
@@ -347,22 +377,41 @@ int gam_encode(gam_handle* h, const float* mel, const int64_t* mel_len, int32_t 
     launch_sub_lengths(reinterpret_cast<const long long*>(mel_len), B, 2 * ((c.subs_kernel_size - 1) / 2) - c.subs_kernel_size,
                        static_cast<int>(M), p->len0, p->len1, p->len2, s);
   }
-  {
-    PROF(PC_SUB_CONV1);
-    rc |= launch_subsample_conv1(mel, p->len0, p->len1, h->w.sub1_w, h->w.sub1_b, p->s1, B, static_cast<int>(M), c.feat_in,
-                                 p->T1, p->F1, d, s);
-  }
-  {
-    PROF(PC_GEMM_CONV2);
-    rc |= launch_gemm_conv(&p->m_s1, &h->m_sub2_w, B, p->T2, d, d, h->w.sub2_b, p->len2, p->s2, d, nsm, s);
-  }
-  GAM_CHECK_LAUNCH(h, "subsampling");
-  if (rc) return fail(h, -4, "subsampling launch rejected (rc=%d)", rc);
-
   float* xdst = (L == 0) ? enc : p->x;  // n_layers_run == 0 -> return pre_encode output
-  {
-    PROF(PC_GEMM_SUBOUT);
-    rc |= launch_gemm(GEMM_BIAS_F32, &p->m_s2, &h->m_sub_out_w, R, d, p->F2 * d, h->w.sub_out_b, nullptr, xdst, d, 1.f, nsm, s);
+  if (c.subsampling == 0) {
+    {
+      PROF(PC_SUB_CONV1);
+      rc |= launch_subsample_conv1(mel, p->len0, p->len1, h->w.sub1_w, h->w.sub1_b, p->s1, B, static_cast<int>(M), c.feat_in,
+                                   p->T1, p->F1, d, s);
+    }
+    {
+      PROF(PC_GEMM_CONV2);
+      rc |= launch_gemm_conv(&p->m_s1, &h->m_sub2_w, B, p->T2, d, d, h->w.sub2_b, p->len2, p->s2, d, nsm, s);
+    }
+    GAM_CHECK_LAUNCH(h, "subsampling");
+    if (rc) return fail(h, -4, "subsampling launch rejected (rc=%d)", rc);
+    {
+      PROF(PC_GEMM_SUBOUT);
+      rc |= launch_gemm(GEMM_BIAS_F32, &p->m_s2, &h->m_sub_out_w, R, d, p->F2 * d, h->w.sub_out_b, nullptr, xdst, d, 1.f, nsm, s);
+    }
+  } else {
+    // conv1d subsampling (gigaam/encoder.py:59-70 with Conv1d): two k-tap / stride-2 implicit GEMMs over time-major data
+    {
+      PROF(PC_SUB_CONV1);
+      launch_mel_to_tmajor_f16(mel, p->len0, p->melT, B, c.feat_in, static_cast<int>(M), s);
+    }
+    {
+      PROF(PC_GEMM_CONV2);
+      rc |= launch_gemm_conv1d(&p->m_melT, &h->m_sub2_w, B, p->T1, c.feat_in, c.subs_kernel_size, d, h->w.c1d_b1, p->len1, p->s1, d,
+                               0, nsm, s);
+    }
+    {
+      PROF(PC_GEMM_SUBOUT);
+      rc |= launch_gemm_conv1d(&p->m_s1_3d, &h->m_sub_out_w, B, p->T2, d, c.subs_kernel_size, d, h->w.c1d_b2, p->len2, xdst, d, 1,
+                               nsm, s);
+    }
+    GAM_CHECK_LAUNCH(h, "subsampling");
+    if (rc) return fail(h, -4, "conv1d subsampling launch rejected (rc=%d)", rc);
   }
   if (L > 0) {
     PROF(PC_LAYERNORM);

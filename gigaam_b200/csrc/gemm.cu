@@ -115,4 +115,34 @@ int launch_gemm_conv(const CUtensorMap* ta4, const CUtensorMap* tw, int B, int T
   return launch_one<EPI_CONV_RELU_MASK_F16, A_CONV>(ta4, tw, p, num_sms, s);
 }
 
+// k-tap / stride-2 conv1d over time-major [B, T_in, C_in] as an implicit GEMM (3-D strided TMA), K order (tap, c).
+// out rows = (b, t_out); fp16 (intermediate stage) or fp32 (last stage = encoder input) with ReLU + time mask.
+int launch_gemm_conv1d(const CUtensorMap* ta3, const CUtensorMap* tw, int B, int T_out, int C_in, int taps, int N,
+                       const float* bias, const int* len_out, void* out, int ldo, int f32_out, int num_sms, cudaStream_t s) {
+  if (N % kBN != 0 || C_in % kGemmBK != 0 || taps < 1) return -1;
+  GemmParams p{};
+  p.N = N;
+  p.conv_T2 = T_out;
+  p.conv_tiles_per_utt = (T_out + 127) / 128;
+  p.conv_kchunks = C_in / kGemmBK;
+  p.conv_len2 = len_out;
+  p.conv_num_blocks = B * p.conv_tiles_per_utt;
+  p.conv_pad = (taps - 1) / 2;
+  p.num_m_tiles = p.conv_num_blocks;
+  p.num_n_tiles = N / kBN;
+  p.num_k_blocks = taps * p.conv_kchunks;
+  p.bias = bias;
+  p.out = out;
+  p.ldo = ldo;
+  p.scale = 1.f;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(gemm2_f16_tn_kernel<EPI_CONV_RELU_MASK_F16, A_CONV1D>, cudaFuncAttributeMaxDynamicSharedMemorySize, kG2Smem);
+    cudaFuncSetAttribute(gemm2_f16_tn_kernel<EPI_CONV_RELU_MASK_F32, A_CONV1D>, cudaFuncAttributeMaxDynamicSharedMemorySize, kG2Smem);
+    attr = true;
+  }
+  return f32_out ? launch_v2<EPI_CONV_RELU_MASK_F32, A_CONV1D>(ta3, tw, p, num_sms, s)
+                 : launch_v2<EPI_CONV_RELU_MASK_F16, A_CONV1D>(ta3, tw, p, num_sms, s);
+}
+
 }  // namespace gam

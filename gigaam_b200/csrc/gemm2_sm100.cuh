@@ -95,12 +95,22 @@ gemm2_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           conv_b = m_blk / p.conv_tiles_per_utt;   // == B for the idle block of an odd count: OOB -> zero fill
           conv_t0 = (m_blk % p.conv_tiles_per_utt) * 8;
         }
+        if constexpr (AMODE == A_CONV1D) {
+          conv_b = m_blk / p.conv_tiles_per_utt;
+          conv_t0 = (m_blk % p.conv_tiles_per_utt) * 128;
+        }
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * kG2StageBytes);
           else ptx::mbar_arrive_cluster(&full_bar[stage], 0);
           if constexpr (AMODE == A_2D) {
             ptx::tma_load_2d_2sm(smem_a + stage * kG2ABytes, &tmap_a, &full_bar[stage], kb * kGemmBK, m_blk * 128);
+          } else if constexpr (AMODE == A_CONV1D) {
+            const int tap = kb / p.conv_kchunks;
+            const int c0 = (kb % p.conv_kchunks) * kGemmBK;
+            // 128 output frames t0.. read input frames 2 t + tap - pad: box of 256 input frames traversed with stride 2
+            ptx::tma_load_3d_2sm(smem_a + stage * kG2ABytes, &tmap_a, &full_bar[stage], c0, 2 * conv_t0 + tap - p.conv_pad,
+                                 conv_b);
           } else {
             const int tap = kb / p.conv_kchunks;
             const int c0 = (kb % p.conv_kchunks) * kGemmBK;
@@ -177,10 +187,21 @@ gemm2_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       long long warp_row0;     // global output row of row 0 of this warp's 32
       int rows_valid;          // how many of the 32 rows exist
       bool row_live = true;    // conv: thread's own row lies inside the utterance's valid length
+      [[maybe_unused]] int rows_live = 32;   // conv1d: how many of the warp's 32 rows are inside the valid length
       if constexpr (AMODE == A_2D) {
         warp_row0 = static_cast<long long>(m_blk) * 128 + quad * 32;
         const long long rem = static_cast<long long>(p.M) - warp_row0;
         rows_valid = rem >= 32 ? 32 : (rem > 0 ? static_cast<int>(rem) : 0);
+      } else if constexpr (AMODE == A_CONV1D) {
+        const bool blk_ok = m_blk < p.conv_num_blocks;
+        const int b = blk_ok ? m_blk / p.conv_tiles_per_utt : 0;
+        const int t0 = (m_blk % p.conv_tiles_per_utt) * 128 + quad * 32;   // this warp: 32 consecutive output frames
+        warp_row0 = static_cast<long long>(b) * p.conv_T2 + t0;
+        const int tv = p.conv_T2 - t0;
+        rows_valid = blk_ok ? (tv >= 32 ? 32 : (tv > 0 ? tv : 0)) : 0;
+        const int lv = blk_ok ? p.conv_len2[b] - t0 : 0;
+        rows_live = lv >= 32 ? 32 : (lv > 0 ? lv : 0);
+        row_live = lane < rows_live;
       } else {
         const bool blk_ok = m_blk < p.conv_num_blocks;   // odd block count: the pair's second CTA idles on the last tile
         const int b = blk_ok ? m_blk / p.conv_tiles_per_utt : 0;
@@ -209,7 +230,7 @@ gemm2_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       __syncwarp();
       const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(quad * 32) << 16);
 
-      if constexpr (EPI == EPI_BIAS_RES_F32 || EPI == EPI_BIAS_F32) {
+      if constexpr (EPI == EPI_BIAS_RES_F32 || EPI == EPI_BIAS_F32 || EPI == EPI_CONV_RELU_MASK_F32) {
         float* outp = reinterpret_cast<float*>(p.out);
 #pragma unroll
         for (int ci = 0; ci < 4; ++ci) {
@@ -246,6 +267,11 @@ gemm2_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 const float4 x = rr[ci & 1][i];
                 a.x = fmaf(p.scale, a.x, x.x); a.y = fmaf(p.scale, a.y, x.y);
                 a.z = fmaf(p.scale, a.z, x.z); a.w = fmaf(p.scale, a.w, x.w);
+              }
+              if constexpr (EPI == EPI_CONV_RELU_MASK_F32) {
+                const bool lv = r < rows_live;
+                a.x = lv ? fmaxf(a.x, 0.f) : 0.f; a.y = lv ? fmaxf(a.y, 0.f) : 0.f;
+                a.z = lv ? fmaxf(a.z, 0.f) : 0.f; a.w = lv ? fmaxf(a.w, 0.f) : 0.f;
               }
               *reinterpret_cast<float4*>(outp + static_cast<size_t>(warp_row0 + r) * p.ldo + col) = a;
             }

@@ -23,10 +23,14 @@ enum GemmEpilogue : int {
   EPI_BIAS_GLU_F16 = 2,    // out16[:, n] = (acc_a + bias_a) * sigmoid(acc_b + bias_b), tile = [a|b]
   EPI_BIAS_RES_F32 = 3,    // out32 = res + scale * (acc + bias)
   EPI_BIAS_F32 = 4,        // out32 = acc + bias
-  EPI_CONV_RELU_MASK_F16 = 5,  // out16 = t2 < len2[b] ? relu(acc + bias) : 0   (A_CONV row mapping)
+  EPI_CONV_RELU_MASK_F16 = 5,  // out16 = t2 < len2[b] ? relu(acc + bias) : 0   (A_CONV / A_CONV1D row mapping)
+  EPI_CONV_RELU_MASK_F32 = 6,  // out32 = t < len[b] ? relu(acc + bias) : 0      (A_CONV1D, last subsampling stage)
 };
 
-enum GemmAMode : int { A_2D = 0, A_CONV = 1 };
+// A_CONV  : implicit im2col of a 3x3 / stride-2 conv2d over channels-last [B, T1, F1, C]  (4-D strided TMA)
+// A_CONV1D: implicit im2col of a k-tap / stride-2 conv1d over time-major [B, T_in, C]      (3-D strided TMA);
+//           a 128-row block = 128 consecutive output frames of one utterance
+enum GemmAMode : int { A_2D = 0, A_CONV = 1, A_CONV1D = 2 };
 
 struct GemmParams {
   int M;             // valid rows of D (A_2D) ; unused for A_CONV
@@ -44,6 +48,7 @@ struct GemmParams {
   int conv_tiles_per_utt; // ceil(T2 / 8)
   int conv_kchunks;       // C / 64
   int conv_num_blocks;    // B * conv_tiles_per_utt  (128-row blocks that exist)
+  int conv_pad;           // A_CONV1D: (taps - 1) / 2
   const int* conv_len2;   // [B] valid output time steps
 };
 

@@ -59,7 +59,12 @@ int launch_gemm(int kind, const CUtensorMap* tmap_a, const CUtensorMap* tmap_w, 
 // implicit-GEMM 3x3/s2 conv over channels-last [B,T1,F1,C] (tmap_a 4-D strided), output [B*T2*16, N] fp16
 int launch_gemm_conv(const CUtensorMap* tmap_a4d, const CUtensorMap* tmap_w, int B, int T2, int C, int N, const float* bias,
                      const int* len2, void* out, int ldo, int num_sms, cudaStream_t s);
+// implicit-GEMM k-tap/s2 conv1d over time-major [B,T_in,C_in] (tmap_a 3-D strided); out [B*T_out, N] fp16 or fp32
+int launch_gemm_conv1d(const CUtensorMap* tmap_a3d, const CUtensorMap* tmap_w, int B, int T_out, int C_in, int taps, int N,
+                       const float* bias, const int* len_out, void* out, int ldo, int f32_out, int num_sms, cudaStream_t s);
 int gemm_init();
+// mel [B, F, M] f32 -> time-major fp16 [B, M, F] with frames >= len zeroed (conv1d subsampling input)
+void launch_mel_to_tmajor_f16(const float* mel, const int* len0, __half* out, int B, int F, int M, cudaStream_t s);
 
 // tensor maps (gam_api.cu)
 int make_tmap_2d_f16(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems, uint32_t box_rows,

@@ -80,8 +80,6 @@ class Engine:
         self.d_ff = self.d_model * enc["ff_expansion_factor"]
         if enc["self_attention_model"] != "rotary":
             raise NotImplementedError("rel_pos self-attention (v1_* checkpoints) is not built yet")
-        if enc["subsampling"] != "conv2d":
-            raise NotImplementedError("conv1d subsampling (v3_* checkpoints) is not built yet")
         self.head_type = 0
         self.num_classes = 0
         self.max_symbols = 10
@@ -141,6 +139,14 @@ class Engine:
     def _pack_subsampling(self, gw, sd, enc):
         p = "encoder.pre_encode."
         d = self.d_model
+        if enc["subsampling"] == "conv1d":
+            # Conv1d weights [out, in, k] -> (out, k, in): K order (tap, channel) of the implicit GEMM
+            for i, name in ((0, "c1d_w1"), (2, "c1d_w2")):
+                w = sd[f"{p}conv.{i}.weight"].float()
+                setattr(gw, name, self._dev(w.permute(0, 2, 1).reshape(w.shape[0], -1), torch.float16))
+            gw.c1d_b1 = self._dev(sd[p + "conv.0.bias"].float())
+            gw.c1d_b2 = self._dev(sd[p + "conv.2.bias"].float())
+            return
         w1 = sd[p + "conv.0.weight"].float()                     # [C, 1, 3, 3]
         gw.sub1_w = self._dev(w1.reshape(d, 9))
         gw.sub1_b = self._dev(sd[p + "conv.0.bias"].float())

@@ -23,7 +23,7 @@ assert len(_CHAR_VOCAB) == 33
 
 # blank-logit bias added to head.joint.joint_net.1.bias[blank]; calibrated with oracle/calibrate_rnnt.py
 # (random weights otherwise emit max_symbols tokens on every frame).
-RNNT_BLANK_BIAS = {"v2_rnnt": 7.45, "v3_e2e_rnnt": 7.45}
+RNNT_BLANK_BIAS = {"v2_rnnt": 7.45, "v3_e2e_rnnt": 23.3, "v3_rnnt": 7.45}
 
 
 def _encoder_cfg(version: str) -> Dict:

@@ -104,6 +104,11 @@ typedef struct gam_weights {
   const float* rnnt_bp;
   const float* rnnt_wo;        /* f [V+1, joint_hidden] joint.joint_net.1.weight */
   const float* rnnt_bo;
+  /* subsampling (conv1d, v3 checkpoints): weights permuted to (out, tap, in) */
+  const void* c1d_w1;  /* h [d, k * feat_in]  encoder.pre_encode.conv.0.weight */
+  const float* c1d_b1; /* f [d] */
+  const void* c1d_w2;  /* h [d, k * d]        encoder.pre_encode.conv.2.weight */
+  const float* c1d_b2; /* f [d] */
 } gam_weights;
 
 int gam_create(const gam_config* cfg, const gam_weights* w, int device, gam_handle** out);

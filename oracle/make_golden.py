@@ -127,3 +127,5 @@ if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count() or 8)
     run_case("v2_ctc", batch=2, seconds=2.0, ragged=True, out_name="v2_ctc_b2_2s.npz")
     run_case("v2_rnnt", batch=2, seconds=2.0, ragged=True, out_name="v2_rnnt_b2_2s.npz")
+    # v3 shape (RECALLED): conv1d k5 subsampling, LayerNorm conv-norm, depthwise k5, n_fft 320, center=False
+    run_case("v3_e2e_rnnt", batch=2, seconds=2.0, ragged=True, out_name="v3_e2e_rnnt_b2_2s.npz")

@@ -318,3 +318,47 @@ def test_config3_rnnt_full_size_runs(dev, v2_rnnt_ckpt):
     n = int(counts[0])
     assert n > 0 and ids[0, :n].tolist() == want[0][0] and frames[0, :n].tolist() == want[0][1]
     assert bool((counts <= 376 * 10).all())
+
+
+# ------------------------------------------------------------------------------------------ v3 shape (conv1d / LN conv-norm / k5 / n_fft 320)
+@pytest.fixture(scope="session")
+def v3_ckpt():
+    return synthetic.synthetic_checkpoint("v3_e2e_rnnt", seed=0)
+
+
+@pytest.fixture(scope="session")
+def eng_v3(dev, v3_ckpt):
+    return Engine(v3_ckpt["cfg"], v3_ckpt["state_dict"], dev)
+
+
+def test_v3_frontend_and_encoder_against_reference_golden(eng_v3, v3_ckpt, golden_dir):
+    """conv1d subsampling as two strided-TMA implicit GEMMs, LayerNorm conv-norm, depthwise k=5, center=False log-mel."""
+    g = np.load(golden_dir / "v3_e2e_rnnt_b2_2s.npz")
+    cfg, sd = v3_ckpt["cfg"], v3_ckpt["state_dict"]
+    wav, wav_len = synthetic.synthetic_audio(2, 2.0, seed=1234, ragged=True)
+    mel = eng_v3.logmel(wav.cuda())
+    assert mel.shape == g["mel"].shape
+    assert float((mel.cpu() - torch.from_numpy(g["mel"])).abs().max()) < 5e-3
+    mel_len = torch.from_numpy(g["mel_len"])
+    with torch.inference_mode():
+        _, len_o, stages = orc.encoder_forward(torch.from_numpy(g["mel"]), mel_len, sd, cfg["encoder"], return_all=True)
+    valid = torch.arange(stages[0].shape[1])[None, :] < len_o[:, None]
+    for n in (0, 1, 16):
+        enc, enc_len = eng_v3.encode(torch.from_numpy(g["mel"]).cuda(), mel_len.cuda(), n_layers_run=n)
+        assert np.array_equal(enc_len.cpu().numpy(), g["enc_len"])
+        assert rel(enc.cpu()[valid], stages[n][valid]) < ENC_REL_TOL, f"v3 after {n} layers"
+    want = torch.from_numpy(g["enc"]).transpose(1, 2)
+    assert rel(enc.cpu()[valid], want[valid]) < ENC_REL_TOL
+
+
+def test_v3_rnnt_greedy_matches_reference_golden(eng_v3, golden_dir):
+    g = np.load(golden_dir / "v3_e2e_rnnt_b2_2s.npz")
+    enc = torch.from_numpy(g["enc"]).transpose(1, 2).contiguous()
+    ids, frames, counts = eng_v3.greedy(enc.cuda(), torch.from_numpy(g["enc_len"]).cuda())
+    total = 0
+    for b in range(2):
+        n = int(counts[b])
+        total += n
+        assert ids[b, :n].tolist() == g[f"ids_{b}"].tolist()
+        assert frames[b, :n].tolist() == g[f"frames_{b}"].tolist()
+    assert total > 0
