@@ -499,6 +499,22 @@ int gam_rnnt_greedy(gam_handle* h, const float* enc, const int32_t* enc_len, int
   { PROF(PC_RNNT_ENCPROJ);
     launch_sgemm_tn_bias(enc, h->w.rnnt_enc_w, h->w.rnnt_enc_b, encproj, static_cast<int>(R), c.joint_hidden, c.d_model, s); }
   PROF(PC_RNNT_GREEDY);
+  static int rnnt_v1 = -1;
+  if (rnnt_v1 < 0) {
+    const char* e = getenv("GAM_RNNT_V1");
+    rnnt_v1 = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (!rnnt_v1) {
+    const int rc = launch_rnnt_greedy_cluster(encproj, enc_len, h->w.rnnt_emb_gates, h->w.rnnt_whh_t, h->w.rnnt_wp_t, h->w.rnnt_bp,
+                                              h->w.rnnt_wo, h->w.rnnt_bo, B, T, c.pred_hidden, c.num_classes, c.num_classes - 1,
+                                              c.max_symbols, max_out, ids, frames, counts, s);
+    if (rc == 0) {
+      GAM_CHECK_LAUNCH(h, "rnnt_greedy_cluster");
+      return 0;
+    }
+    if (rc < 0) return fail(h, -4, "rnnt cluster kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    // rc == 1: no 16-CTA clusters on this device / unsupported hidden size -> per-utterance kernel below
+  }
   if (launch_rnnt_greedy(encproj, enc_len, h->w.rnnt_emb_gates, h->w.rnnt_whh_t, h->w.rnnt_wp_t, h->w.rnnt_bp, h->w.rnnt_wo,
                          h->w.rnnt_bo, B, T, c.pred_hidden, c.num_classes, c.num_classes - 1, c.max_symbols, max_out, ids,
                          frames, counts, s) != 0)

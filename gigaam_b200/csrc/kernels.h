@@ -43,6 +43,11 @@ int launch_rnnt_greedy(const float* encproj, const int* len, const float* emb_ga
                        const float* bp, const float* wo, const float* bo, int B, int T, int H, int V1, int blank,
                        int max_symbols, int max_out, int* ids, int* frames, int* counts, cudaStream_t s);
 
+// rnnt_cluster.cu: returns 0 ok, 1 = 16-CTA clusters unavailable / unsupported shape (use launch_rnnt_greedy), <0 error
+int launch_rnnt_greedy_cluster(const float* encproj, const int* len, const float* emb_gates, const float* whhT, const float* wpT,
+                               const float* bp, const float* wo, const float* bo, int B, int T, int H, int V1, int blank,
+                               int max_symbols, int max_out, int* ids, int* frames, int* counts, cudaStream_t s);
+
 // gemm.cu
 struct GemmParams;
 enum GemmKind : int {
