@@ -636,9 +636,255 @@ __global__ void __launch_bounds__(64 + 256, 1) attention_persistent_kernel(const
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Long-sequence variant (any T <= 640, used for T > 256): one CTA per (utterance, head) keeps ALL K / V blocks of
+// the head resident in shared memory and walks the query tiles; two softmax warpgroups (each with its own MMA
+// issuer warp, S slot, P alias and O accumulator in TMEM) process alternate query tiles concurrently.  A score
+// row no longer fits TMEM, so each query tile makes two sweeps over the key blocks (max, then exp / P.V) with
+// S recomputed in the second sweep: tensor time is cheap here, the exp throughput (MUFU) is the bound.
+struct AttnLongParams {
+  int T, nkb, H;
+  const int* klen;
+  __half* out;
+  int ld_out, dk;
+  float scale_log2;
+};
+
+constexpr int kLongThreads = 384;   // warp 0 TMA, 1/2 MMA issuers, 3 TMEM owner, 4-7 / 8-11 softmax warpgroups
+
+__global__ void __launch_bounds__(kLongThreads, 1) attention_long_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
+                                                                       const AttnLongParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int nkb = p.nkb;
+  uint8_t* sK = smem;                          // [nkb]
+  uint8_t* sV = sK + nkb * kTileBytes;         // [nkb]
+  uint8_t* sQ = sV + nkb * kTileBytes;         // [2] one per warpgroup
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sQ + 2 * kTileBytes);
+  uint64_t* kv_full = bars;          // [kMaxKB]
+  uint64_t* q_full = bars + kMaxKB;  // [2]
+  uint64_t* q_empty = q_full + 2;    // [2]
+  uint64_t* s_full = q_full + 4;     // [2]
+  uint64_t* s_empty = q_full + 6;    // [2]
+  uint64_t* p_full = q_full + 8;     // [2]
+  uint64_t* o_full = q_full + 10;    // [2]
+  uint64_t* o_empty = q_full + 12;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_full + 14);
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int h = blockIdx.x % p.H, b = blockIdx.x / p.H;
+  const int row0 = b * p.T;
+  const int dmodel = p.ld_out;
+  const int nqt = nkb;
+
+  if (warp_idx == 0 && ptx::elect_one()) {
+    ptx::prefetch_tmap(&tmap_qkv);
+    for (int i = 0; i < kMaxKB; ++i) ptx::mbar_init(&kv_full[i], 1);
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&q_full[i], 1);
+      ptx::mbar_init(&q_empty[i], 1);
+      ptx::mbar_init(&s_full[i], 1);
+      ptx::mbar_init(&s_empty[i], 4);
+      ptx::mbar_init(&p_full[i], 4);
+      ptx::mbar_init(&o_full[i], 1);
+      ptx::mbar_init(&o_empty[i], 4);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp_idx == 3) ptx::tmem_alloc<512>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp_idx == 0) {
+    if (ptx::elect_one()) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        ptx::mbar_arrive_expect_tx(&kv_full[kb], 2 * kTileBytes);
+        ptx::tma_load_2d(sK + kb * kTileBytes, &tmap_qkv, &kv_full[kb], dmodel + h * p.dk, row0 + kb * 128);
+        ptx::tma_load_2d(sV + kb * kTileBytes, &tmap_qkv, &kv_full[kb], 2 * dmodel + h * p.dk, row0 + kb * 128);
+      }
+      for (int qt = 0; qt < nqt; ++qt) {
+        const int wg = qt & 1, it = qt >> 1;
+        ptx::mbar_wait(&q_empty[wg], (it & 1) ^ 1);
+        ptx::mbar_arrive_expect_tx(&q_full[wg], kTileBytes);
+        ptx::tma_load_2d(sQ + wg * kTileBytes, &tmap_qkv, &q_full[wg], h * p.dk, row0 + qt * 128);
+      }
+    }
+  } else if (warp_idx == 1 || warp_idx == 2) {
+    // ===================================================== MMA issuer of warpgroup wg
+    const int wg = warp_idx - 1;
+    constexpr uint32_t kIdescS = ptx::make_idesc_f16(128, 128, 0, 0);
+    constexpr uint32_t kIdescPV = ptx::make_idesc_f16(128, 64, 0, 1);
+    const int ksteps_qk = p.dk / 16;
+    const uint32_t t_s = tmem_base + wg * 256;        // S slot [0,128) (P aliases [0,64)), O at [128,192)
+    const uint32_t qa = ptx::smem_u32(sQ + wg * kTileBytes);
+    int it = 0;
+    for (int qt = wg; qt < nqt; qt += 2, ++it) {
+      ptx::mbar_wait(&q_full[wg], it & 1);
+      ptx::mbar_wait(&o_empty[wg], (it & 1) ^ 1);
+      for (int pass = 0; pass < 2; ++pass) {
+        for (int kb = 0; kb < nkb; ++kb) {
+          // The S slot may be overwritten once the softmax warps have read the previous max-sweep tile (they arrive
+          // on s_empty only in sweep 0: phase index it*nkb + kb').  In sweep 1 the slot also holds P, but the next S
+          // MMA is issued by this same thread after the P.V MMAs and the tensor pipe executes them in order.
+          if (pass == 0 && kb > 0) ptx::mbar_wait(s_empty + wg, (it * nkb + kb - 1) & 1);
+          if (pass == 1 && kb == 0) ptx::mbar_wait(s_empty + wg, (it * nkb + nkb - 1) & 1);
+          if (it == 0 && pass == 0) ptx::mbar_wait(&kv_full[kb], 0);
+          ptx::tc_fence_after();
+          if (ptx::elect_one()) {
+            const uint32_t ka = ptx::smem_u32(sK + kb * kTileBytes);
+            for (int k = 0; k < ksteps_qk; ++k)
+              ptx::mma_f16_ss(t_s, ptx::make_smem_desc_sw128(qa + k * 32, 16, 1024), ptx::make_smem_desc_sw128(ka + k * 32, 16, 1024),
+                              kIdescS, k != 0 ? 1u : 0u);
+            ptx::mma_commit(&s_full[wg]);
+          }
+          __syncwarp();
+          if (pass == 1) {
+            ptx::mbar_wait(&p_full[wg], (it * nkb + kb) & 1);
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
+              const uint32_t va = ptx::smem_u32(sV + kb * kTileBytes);
+#pragma unroll
+              for (int ks = 0; ks < 8; ++ks)
+                ptx::mma_f16_ts(t_s + 128, t_s + ks * 8, ptx::make_smem_desc_sw128(va + ks * 2048, 1024, 1024), kIdescPV,
+                                (kb | ks) != 0 ? 1u : 0u);
+              if (kb == nkb - 1) {
+                ptx::mma_commit(&o_full[wg]);
+                ptx::mma_commit(&q_empty[wg]);
+              }
+            }
+            __syncwarp();
+          }
+        }
+      }
+    }
+  } else if (warp_idx >= 4) {
+    // ===================================================== softmax warpgroups
+    const int wg = (warp_idx - 4) >> 2;
+    const int quad = warp_idx & 3;
+    const int lane = threadIdx.x & 31;
+    const int r = quad * 32 + lane;
+    const uint32_t t_s = tmem_base + wg * 256 + (static_cast<uint32_t>(quad * 32) << 16);
+    int klen = p.T;
+    if (p.klen != nullptr) klen = min(max(p.klen[b], 0), p.T);
+    uint32_t n_s = 0;
+    int it = 0;
+    for (int qt = wg; qt < nqt; qt += 2, ++it) {
+      float m = -INFINITY;
+      for (int kb = 0; kb < nkb; ++kb, ++n_s) {
+        ptx::mbar_wait(&s_full[wg], n_s & 1);
+        ptx::tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          const int key0 = kb * 128 + c * 32;
+          if (key0 >= klen) break;
+          uint32_t v[32];
+          ptx::tmem_ld_32x32b_x32(t_s + c * 32, v);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (key0 + j < klen) m = fmaxf(m, __uint_as_float(v[j]));
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(s_empty + wg);
+      }
+      if (m == -INFINITY) m = 0.f;
+      const float mc = m * p.scale_log2;
+      float sum = 0.f;
+      for (int kb = 0; kb < nkb; ++kb, ++n_s) {
+        ptx::mbar_wait(&s_full[wg], n_s & 1);
+        ptx::tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          const int key0 = kb * 128 + c * 32;
+          uint32_t pk[16];
+          if (key0 < klen) {
+            uint32_t v[32];
+            ptx::tmem_ld_32x32b_x32(t_s + c * 32, v);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              const float p0 = (key0 + j < klen) ? ex2(fmaf(__uint_as_float(v[j]), p.scale_log2, -mc)) : 0.f;
+              const float p1 = (key0 + j + 1 < klen) ? ex2(fmaf(__uint_as_float(v[j + 1]), p.scale_log2, -mc)) : 0.f;
+              sum += p0 + p1;
+              __half2 hh = __floats2half2_rn(p0, p1);
+              pk[j >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) pk[j] = 0u;
+          }
+          ptx::tmem_st_32x32b_x16(t_s + c * 16, pk);
+        }
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&p_full[wg]);   // (the P.V commit, not us, releases the slot in this sweep)
+      }
+      ptx::mbar_wait(&o_full[wg], it & 1);
+      ptx::tc_fence_after();
+      uint32_t ov[48];
+      ptx::tmem_ld_32x32b_x16(t_s + 128, ov);
+      ptx::tmem_ld_32x32b_x16(t_s + 144, ov + 16);
+      ptx::tmem_ld_32x32b_x16(t_s + 160, ov + 32);
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&o_empty[wg]);
+      const float inv = sum > 0.f ? 1.0f / sum : 0.f;
+      const int q = qt * 128 + r;
+      if (q < p.T) {
+        __half* dst = p.out + (static_cast<size_t>(row0) + q) * p.ld_out + h * p.dk;
+#pragma unroll
+        for (int c = 0; c < 48; c += 8) {
+          if (c < p.dk) {
+            uint32_t o[4];
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) {
+              __half2 hh = __floats2half2_rn(__uint_as_float(ov[c + j]) * inv, __uint_as_float(ov[c + j + 1]) * inv);
+              o[j >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+            }
+            *reinterpret_cast<uint4*>(dst + c) = make_uint4(o[0], o[1], o[2], o[3]);
+          }
+        }
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 3) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<512>(tmem_base);
+  }
+}
+
 }  // namespace
 
 int attention_smem_bytes(int nkb) { return (3 + 2 * nkb) * kTileBytes + 128 + 1024; }
+
+static int launch_attention_long(const CUtensorMap* tmap_qkv, const int* klen, __half* out, int B, int T, int H, int dk,
+                                 int d_model, cudaStream_t s) {
+  AttnLongParams p;
+  p.T = T;
+  p.nkb = (T + 127) / 128;
+  p.H = H;
+  p.klen = klen;
+  p.out = out;
+  p.ld_out = d_model;
+  p.dk = dk;
+  p.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(dk));
+  static int attr_set = 0;
+  if (!attr_set) {
+    cudaFuncSetAttribute(attention_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_set = 1;
+  }
+  const int smem = (2 * p.nkb + 2) * kTileBytes + 256 + 1024;
+  attention_long_kernel<<<B * H, kLongThreads, smem, s>>>(*tmap_qkv, p);
+  return 0;
+}
 
 static int launch_attention_persistent(const CUtensorMap* tmap_qkv, const int* klen, __half* out, int B, int T, int H, int dk,
                                        int d_model, int num_sms, cudaStream_t s) {
@@ -707,6 +953,7 @@ int launch_attention(const CUtensorMap* tmap_qkv, const int* klen, __half* out, 
   }
   if (nkb <= 2 && !force_v1 && !force_v2)
     return launch_attention_persistent(tmap_qkv, klen, out, B, T, H, dk, d_model, num_sms, s);
+  if (!force_v1 && !force_v2) return launch_attention_long(tmap_qkv, klen, out, B, T, H, dk, d_model, s);
   if (nkb <= kResMaxKB && !force_v1) return launch_attention_resident(tmap_qkv, klen, out, B, T, H, dk, d_model, s);
   AttnParams p;
   p.T = T;
