@@ -36,7 +36,7 @@ class GamLayerWeights(C.Structure):
 WEIGHT_FIELDS_HEAD = ("window", "dft_cos", "dft_sin", "mel_fb", "sub1_w", "sub1_b", "sub2_w", "sub2_b",
                       "sub_out_w", "sub_out_b", "rope_cos", "rope_sin")
 WEIGHT_FIELDS_TAIL = ("ctc_w", "ctc_b", "rnnt_enc_w", "rnnt_enc_b", "rnnt_emb_gates", "rnnt_whh_t", "rnnt_wp_t",
-                      "rnnt_bp", "rnnt_wo", "rnnt_bo", "c1d_w1", "c1d_b1", "c1d_w2", "c1d_b2")
+                      "rnnt_bp", "rnnt_wo", "rnnt_bo", "c1d_w1", "c1d_b1", "c1d_w2", "c1d_b2", "dft_w", "mel_lo", "mel_hi")
 
 
 class GamWeights(C.Structure):
@@ -47,7 +47,7 @@ class GamWeights(C.Structure):
 EXPORTS = ("gam_create", "gam_destroy", "gam_last_error", "gam_version", "gam_logmel_frames", "gam_encoded_frames",
            "gam_workspace_bytes", "gam_logmel", "gam_encode", "gam_ctc_greedy", "gam_rnnt_greedy", "gam_test_gemm",
            "gam_test_attention", "gam_launch_count", "gam_profile_begin", "gam_profile_end", "gam_profile_class_count",
-           "gam_profile_class_name")
+           "gam_profile_class_name", "gam_logmel_workspace_bytes", "gam_logmel_tc")
 
 
 def lib_path() -> Path:
@@ -92,6 +92,10 @@ def load() -> C.CDLL:
     lib.gam_test_gemm.restype = C.c_int
     lib.gam_test_attention.argtypes = [H, c_vp, c_vp, c_vp, i32, i32, c_vp]
     lib.gam_test_attention.restype = C.c_int
+    lib.gam_logmel_workspace_bytes.argtypes = [H, i32, i64]
+    lib.gam_logmel_workspace_bytes.restype = i64
+    lib.gam_logmel_tc.argtypes = [H, c_vp, i32, i64, c_vp, c_vp, i64, c_vp]
+    lib.gam_logmel_tc.restype = C.c_int
     lib.gam_profile_begin.argtypes = [H]
     lib.gam_profile_begin.restype = C.c_int
     lib.gam_profile_end.argtypes = [H, C.POINTER(C.c_double), C.POINTER(C.c_int64), i32]

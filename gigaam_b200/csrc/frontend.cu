@@ -209,7 +209,98 @@ __global__ void __launch_bounds__(256) mel_to_tmajor_f16_kernel(const float* __r
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Tensor-core front end.  The real DFT of every windowed frame is a GEMM  X = F . D^T  (F: frames x n_fft,
+// D: cos|sin basis); fp16 alone would bury quiet bins under rounding noise, so both operands are split into
+// fp16 (hi, lo) pairs and the three significant products are folded into ONE GEMM by concatenating along K:
+//   A' = [ f_hi | f_lo | f_hi ],   W' = [ d_hi | d_hi | d_lo ]     (K = 3 * Kp, ~22-bit effective mantissas)
+// run on the CTA-pair tcgen05 kernel with the power epilogue (re^2 + im^2).  This kernel builds A'.
+__global__ void __launch_bounds__(256) frames_split_kernel(const float* __restrict__ wav, int n_samples, int n_frames,
+                                                           const float* __restrict__ window, __half* __restrict__ A, int n_fft,
+                                                           int Kp, int hop, int center) {
+  const int b = blockIdx.y;
+  const int frame = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (frame >= n_frames) return;
+  const int lane = threadIdx.x & 31;
+  const float* x = wav + static_cast<size_t>(b) * n_samples;
+  __half* row = A + (static_cast<size_t>(b) * n_frames + frame) * (3 * Kp);
+  const int half = n_fft / 2;
+  for (int i2 = lane; i2 < Kp / 2; i2 += 32) {
+    float v[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int j = 2 * i2 + e;
+      float s = 0.f;
+      if (j < n_fft) {
+        int idx = frame * hop + j - (center ? half : 0);
+        if (center) {
+          if (idx < 0) idx = -idx;
+          if (idx >= n_samples) idx = 2 * (n_samples - 1) - idx;
+        }
+        if (idx >= 0 && idx < n_samples) s = x[idx] * __ldg(window + j);
+      }
+      v[e] = s;
+    }
+    const __half2 hi = __floats2half2_rn(v[0], v[1]);
+    const float2 hf = __half22float2(hi);
+    const __half2 lo = __floats2half2_rn(v[0] - hf.x, v[1] - hf.y);
+    reinterpret_cast<__half2*>(row)[i2] = hi;
+    reinterpret_cast<__half2*>(row + Kp)[i2] = lo;
+    reinterpret_cast<__half2*>(row + 2 * Kp)[i2] = hi;
+  }
+}
+
+// power spectrum [F, ldp] f32 -> log(clamp(P . fb)) written as [B, n_mels, M] (gigaam/preprocess.py:49-50, MelScale).
+// block = 32 frames of one utterance; thread = (mel m, 8 frames); the HTK triangles are sparse, so each mel filter only
+// walks its own bin range [lo_m, hi_m).
+__global__ void __launch_bounds__(256) mel_log_kernel(const float* __restrict__ P, int ldp, int n_frames, int nbins,
+                                                      const float* __restrict__ fb, const int* __restrict__ mel_lo,
+                                                      const int* __restrict__ mel_hi, float* __restrict__ mel, int n_mels) {
+  __shared__ float ps[32][257];
+  __shared__ float ot[64][33];
+  const int b = blockIdx.y;
+  const int f0 = blockIdx.x * 32;
+  for (int i = threadIdx.x; i < 32 * 64; i += 256) {
+    const int fr = i / 64, c4 = (i % 64) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (f0 + fr < n_frames && c4 < ldp) v = *reinterpret_cast<const float4*>(P + (static_cast<size_t>(b) * n_frames + f0 + fr) * ldp + c4);
+    ps[fr][c4] = v.x; ps[fr][c4 + 1] = v.y; ps[fr][c4 + 2] = v.z; ps[fr][c4 + 3] = v.w;
+  }
+  __syncthreads();
+  const int m = threadIdx.x & 63, fg = threadIdx.x >> 6;
+  if (m < n_mels) {
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    const int lo = mel_lo[m], hi = min(mel_hi[m], nbins);
+    for (int k = lo; k < hi; ++k) {
+      const float w = __ldg(fb + static_cast<size_t>(k) * n_mels + m);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = fmaf(ps[fg * 8 + i][k], w, acc[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ot[m][fg * 8 + i] = logf(fminf(fmaxf(acc[i], 1e-9f), 1e9f));
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n_mels * 32; i += 256) {
+    const int mm = i / 32, fr = i % 32;
+    if (f0 + fr < n_frames) mel[(static_cast<size_t>(b) * n_mels + mm) * n_frames + f0 + fr] = ot[mm][fr];
+  }
+}
+
 }  // namespace
+
+void launch_frames_split(const float* wav, int B, int n_samples, int n_frames, const float* window, __half* A, int n_fft, int Kp,
+                         int hop, int center, cudaStream_t s) {
+  dim3 grid((n_frames + 7) / 8, B);
+  frames_split_kernel<<<grid, 256, 0, s>>>(wav, n_samples, n_frames, window, A, n_fft, Kp, hop, center);
+}
+
+void launch_mel_log(const float* P, int ldp, int B, int n_frames, int nbins, const float* fb, const int* mel_lo, const int* mel_hi,
+                    float* mel, int n_mels, cudaStream_t s) {
+  dim3 grid((n_frames + 31) / 32, B);
+  mel_log_kernel<<<grid, 256, 0, s>>>(P, ldp, n_frames, nbins, fb, mel_lo, mel_hi, mel, n_mels);
+}
 
 void launch_mel_to_tmajor_f16(const float* mel, const int* len0, __half* out, int B, int F, int M, cudaStream_t s) {
   dim3 grid((M + 31) / 32, (F + 31) / 32, B);

@@ -103,6 +103,9 @@ struct gam_handle {
   std::vector<gam_layer_weights> layers;
   std::vector<LayerMaps> lmaps;
   CUtensorMap m_sub2_w, m_sub_out_w;
+  CUtensorMap m_dft_w, m_lm_a;   // tensor-core front end: split DFT basis / frame matrix (cached per workspace)
+  const void* lm_A = nullptr;
+  int64_t lm_F = 0;
   int device = 0;
   int num_sms = 148;
   int64_t launches = 0;
@@ -316,6 +319,10 @@ int gam_create(const gam_config* cfg, const gam_weights* w, int device, gam_hand
     rc |= make_tmap_2d_f16(&h->m_sub2_w, w->c1d_w1, d, k1, k1, 128, 64);        // stage 1: [d, taps * feat_in]
     rc |= make_tmap_2d_f16(&h->m_sub_out_w, w->c1d_w2, d, k2, k2, 128, 64);     // stage 2: [d, taps * d]
   }
+  if (w->dft_w != nullptr) {
+    const uint64_t kk = 3 * static_cast<uint64_t>((c.n_fft + 63) / 64 * 64);
+    rc |= make_tmap_2d_f16(&h->m_dft_w, w->dft_w, 512, kk, kk, 128, 64);
+  }
   if (rc != 0) return fail(h, -2, "cuTensorMapEncodeTiled failed for weight maps (rc=%d)", rc);
   return 0;
 }
@@ -357,6 +364,51 @@ int gam_logmel(gam_handle* h, const float* wav, int32_t B, int64_t n_samples, fl
       return fail(h, -1, "logmel: unsupported n_fft/n_mels (%d/%d)", c.n_fft, c.n_mels);
   }
   GAM_CHECK_LAUNCH(h, "logmel");
+  return 0;
+}
+
+static inline int logmel_kp(const gam_config& c) { return (c.n_fft + 63) / 64 * 64; }
+
+int64_t gam_logmel_workspace_bytes(const gam_handle* h, int32_t B, int64_t n_samples) {
+  const int64_t F = static_cast<int64_t>(B) * gam_logmel_frames(h, n_samples);
+  return align_up(F * 3 * logmel_kp(h->cfg) * 2, 1024) + align_up(F * 256 * 4, 1024) + 2048;
+}
+
+int gam_logmel_tc(gam_handle* h, const float* wav, int32_t B, int64_t n_samples, float* mel, void* workspace,
+                  int64_t workspace_bytes, void* stream) {
+  const gam_config& c = h->cfg;
+  if (!h->w.dft_w || !h->w.mel_lo || !h->w.mel_hi) return fail(h, -1, "logmel_tc: split DFT basis not provided");
+  if (c.n_fft / 2 + 1 > 256) return fail(h, -1, "logmel_tc: n_fft %d exceeds 256 bins", c.n_fft);
+  const int64_t M = gam_logmel_frames(h, n_samples);
+  if (M <= 0) return fail(h, -1, "waveform too short: %lld samples", (long long)n_samples);
+  if (c.center && n_samples <= c.n_fft / 2) return fail(h, -1, "reflect padding needs more than n_fft/2 samples");
+  if (workspace_bytes < gam_logmel_workspace_bytes(h, B, n_samples)) return fail(h, -1, "logmel_tc: workspace too small");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int Kp = logmel_kp(c);
+  const int64_t F = static_cast<int64_t>(B) * M;
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~uintptr_t(1023));
+  __half* A = reinterpret_cast<__half*>(ws);
+  float* P = reinterpret_cast<float*>(ws + align_up(F * 3 * Kp * 2, 1024));
+  if (h->lm_A != A || h->lm_F != F) {
+    if (make_tmap_2d_f16(&h->m_lm_a, A, F, 3 * Kp, 3 * Kp, 128, 64) != 0) return fail(h, -2, "logmel_tc: tensor map encode failed");
+    h->lm_A = A;
+    h->lm_F = F;
+  }
+  {
+    PROF(PC_LOGMEL);
+    launch_frames_split(wav, B, static_cast<int>(n_samples), static_cast<int>(M), h->w.window, A, c.n_fft, Kp, c.hop_length, c.center, s);
+  }
+  {
+    PROF(PC_LOGMEL);
+    if (launch_gemm_power(&h->m_lm_a, &h->m_dft_w, static_cast<int>(F), 512, 3 * Kp, P, 256, h->num_sms, s) != 0)
+      return fail(h, -4, "logmel_tc: DFT GEMM launch rejected");
+  }
+  {
+    PROF(PC_LOGMEL);
+    launch_mel_log(P, 256, B, static_cast<int>(M), c.n_fft / 2 + 1, h->w.mel_fb, h->w.mel_lo, h->w.mel_hi, mel, c.n_mels, s);
+  }
+  GAM_CHECK_LAUNCH(h, "logmel_tc");
   return 0;
 }
 

@@ -115,6 +115,27 @@ int launch_gemm_conv(const CUtensorMap* ta4, const CUtensorMap* tw, int B, int T
   return launch_one<EPI_CONV_RELU_MASK_F16, A_CONV>(ta4, tw, p, num_sms, s);
 }
 
+// power spectrum of a split-precision DFT: D = A W^T with W tiles [128 cos | 128 sin]; out[:, N/2] = re^2 + im^2
+int launch_gemm_power(const CUtensorMap* ta, const CUtensorMap* tw, int M, int N, int K, float* out, int ldo, int num_sms,
+                      cudaStream_t s) {
+  if (N % kBN != 0 || K % kGemmBK != 0 || M <= 0) return -1;
+  GemmParams p{};
+  p.M = M;
+  p.N = N;
+  p.num_m_tiles = (M + kGemmBM - 1) / kGemmBM;
+  p.num_n_tiles = N / kBN;
+  p.num_k_blocks = K / kGemmBK;
+  p.out = out;
+  p.ldo = ldo;
+  p.scale = 1.f;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(gemm2_f16_tn_kernel<EPI_POWER_F32, A_2D>, cudaFuncAttributeMaxDynamicSharedMemorySize, kG2Smem);
+    attr = true;
+  }
+  return launch_v2<EPI_POWER_F32, A_2D>(ta, tw, p, num_sms, s);
+}
+
 // k-tap / stride-2 conv1d over time-major [B, T_in, C_in] as an implicit GEMM (3-D strided TMA), K order (tap, c).
 // out rows = (b, t_out); fp16 (intermediate stage) or fp32 (last stage = encoder input) with ReLU + time mask.
 int launch_gemm_conv1d(const CUtensorMap* ta3, const CUtensorMap* tw, int B, int T_out, int C_in, int taps, int N,

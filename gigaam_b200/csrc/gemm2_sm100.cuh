@@ -171,7 +171,7 @@ gemm2_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const int n_blk = tile % p.num_n_tiles;
       const int m_blk = m_pair * 2 + static_cast<int>(rank);
       // this warp's 128 bias values -> smem for broadcast reads
-      {
+      if constexpr (EPI != EPI_POWER_F32) {
         const float* bsrc = p.bias + n_blk * BN;
         float4 bv;
         if constexpr (EPI == EPI_BIAS_GLU_F16) {
@@ -275,6 +275,36 @@ gemm2_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               }
               *reinterpret_cast<float4*>(outp + static_cast<size_t>(warp_row0 + r) * p.ldo + col) = a;
             }
+          }
+          __syncwarp();
+        }
+      } else if constexpr (EPI == EPI_POWER_F32) {
+        // |X|^2 of a DFT whose cos rows fill accumulator columns [0,128) and sin rows [128,256) of the tile
+        float* outp = reinterpret_cast<float*>(p.out);
+#pragma unroll 1
+        for (int ci = 0; ci < 2; ++ci) {
+          const int c = half * 64 + ci * 32;
+          uint32_t va[32], vb[32];
+          ptx::tmem_ld_32x32b_x32(taddr + c, va);
+          ptx::tmem_ld_32x32b_x32(taddr + 128 + c, vb);
+          ptx::tmem_ld_wait();
+          float4* srow = reinterpret_cast<float4*>(stg + lane * 36);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            float4 o;
+            o.x = __uint_as_float(va[4 * q]) * __uint_as_float(va[4 * q]) + __uint_as_float(vb[4 * q]) * __uint_as_float(vb[4 * q]);
+            o.y = __uint_as_float(va[4 * q + 1]) * __uint_as_float(va[4 * q + 1]) + __uint_as_float(vb[4 * q + 1]) * __uint_as_float(vb[4 * q + 1]);
+            o.z = __uint_as_float(va[4 * q + 2]) * __uint_as_float(va[4 * q + 2]) + __uint_as_float(vb[4 * q + 2]) * __uint_as_float(vb[4 * q + 2]);
+            o.w = __uint_as_float(va[4 * q + 3]) * __uint_as_float(va[4 * q + 3]) + __uint_as_float(vb[4 * q + 3]) * __uint_as_float(vb[4 * q + 3]);
+            srow[q] = o;
+          }
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = i * 4 + (lane >> 3);
+            if (r < rows_valid)
+              *reinterpret_cast<float4*>(outp + static_cast<size_t>(warp_row0 + r) * p.ldo + n_blk * 128 + c + c4) =
+                  *reinterpret_cast<const float4*>(stg + r * 36 + c4);
           }
           __syncwarp();
         }

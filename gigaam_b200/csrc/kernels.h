@@ -67,6 +67,13 @@ int launch_gemm_conv(const CUtensorMap* tmap_a4d, const CUtensorMap* tmap_w, int
 // implicit-GEMM k-tap/s2 conv1d over time-major [B,T_in,C_in] (tmap_a 3-D strided); out [B*T_out, N] fp16 or fp32
 int launch_gemm_conv1d(const CUtensorMap* tmap_a3d, const CUtensorMap* tmap_w, int B, int T_out, int C_in, int taps, int N,
                        const float* bias, const int* len_out, void* out, int ldo, int f32_out, int num_sms, cudaStream_t s);
+int launch_gemm_power(const CUtensorMap* tmap_a, const CUtensorMap* tmap_w, int M, int N, int K, float* out, int ldo, int num_sms,
+                      cudaStream_t s);
+// tensor-core front end helpers (frontend.cu)
+void launch_frames_split(const float* wav, int B, int n_samples, int n_frames, const float* window, __half* A, int n_fft, int Kp,
+                         int hop, int center, cudaStream_t s);
+void launch_mel_log(const float* P, int ldp, int B, int n_frames, int nbins, const float* fb, const int* mel_lo, const int* mel_hi,
+                    float* mel, int n_mels, cudaStream_t s);
 int gemm_init();
 // mel [B, F, M] f32 -> time-major fp16 [B, M, F] with frames >= len zeroed (conv1d subsampling input)
 void launch_mel_to_tmajor_f16(const float* mel, const int* len0, __half* out, int B, int F, int M, cudaStream_t s);

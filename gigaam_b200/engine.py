@@ -6,6 +6,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -45,6 +46,23 @@ def pack_sub_out_weight(wo: Tensor, channels: int) -> Tensor:
     which the stage-2 conv epilogue writes its [B, T', F2, C] output."""
     f2 = wo.shape[1] // channels
     return wo.reshape(wo.shape[0], channels, f2).permute(0, 2, 1).reshape(wo.shape[0], f2 * channels)
+
+
+def split_dft_basis(n_fft: int) -> Tensor:
+    """fp16 [512, 3*Kp] basis of the real DFT for the K-concatenated split-precision GEMM (Kp = n_fft rounded up to 64).
+    Rows: two 256-row tiles, tile t = [128 cos rows | 128 sin rows] of bins t*128 + j (bins >= n_fft/2+1 are zero rows);
+    columns: [d_hi | d_hi | d_lo] with d = cos / sin(2 pi k i / n_fft), d_hi = fp16(d), d_lo = fp16(d - d_hi)."""
+    kp = (n_fft + 63) // 64 * 64
+    nb = n_fft // 2 + 1
+    k = torch.arange(256, dtype=torch.float64)[:, None]
+    i = torch.arange(kp, dtype=torch.float64)[None, :]
+    ang = 2.0 * math.pi * k * i / n_fft
+    valid = ((k < nb) & (i < n_fft)).double()
+    basis = torch.stack([torch.cos(ang) * valid, torch.sin(ang) * valid], 1)        # [256 bins, 2, kp]
+    rows = basis.view(2, 128, 2, kp).permute(0, 2, 1, 3).reshape(512, kp)          # tile, (cos|sin), bin-in-tile
+    hi = rows.to(torch.float16)
+    lo = (rows - hi.double()).to(torch.float16)
+    return torch.cat([hi, hi, lo], dim=1).contiguous()
 
 
 def rotary_half_tables(dk: int, base: float, max_len: int):
@@ -134,7 +152,19 @@ class Engine:
         gw.window = self._dev(window)
         gw.dft_cos = self._dev(torch.cos(ang).float())
         gw.dft_sin = self._dev(torch.sin(ang).float())
-        gw.mel_fb = self._dev(sd["preprocessor.featurizer.0.mel_scale.fb"].float())
+        fb = sd["preprocessor.featurizer.0.mel_scale.fb"].float()
+        gw.mel_fb = self._dev(fb)
+        # tensor-core front end: split-precision DFT basis + bin range of every mel filter
+        if K <= 256:
+            gw.dft_w = self._dev(split_dft_basis(n))
+            nz = fb != 0
+            lo = torch.where(nz.any(0), nz.float().argmax(0), torch.zeros(fb.shape[1], dtype=torch.long))
+            hi = torch.where(nz.any(0), fb.shape[0] - nz.flip(0).float().argmax(0), torch.zeros(fb.shape[1], dtype=torch.long))
+            gw.mel_lo = self._dev(lo.to(torch.int32))
+            gw.mel_hi = self._dev(hi.to(torch.int32))
+            self._logmel_tc = True
+        else:
+            self._logmel_tc = False
 
     def _pack_subsampling(self, gw, sd, enc):
         p = "encoder.pre_encode."
@@ -247,6 +277,15 @@ class Engine:
         B, N = wav.shape
         M = self.logmel_frames(N)
         mel = torch.empty((B, self.n_mels, M), dtype=torch.float32, device=self.device)
+        if self._logmel_tc and os.environ.get("GAM_LOGMEL_FUSED", "0") != "1":
+            key = ("logmel", B, N)
+            ws = self._ws.get(key)
+            if ws is None:
+                ws = torch.empty(int(self.lib.gam_logmel_workspace_bytes(self.handle, B, N)), dtype=torch.uint8, device=self.device)
+                self._ws[key] = ws
+            rc = self.lib.gam_logmel_tc(self.handle, wav.data_ptr(), B, N, mel.data_ptr(), ws.data_ptr(), ws.numel(), self._stream())
+            _lib.check(self.lib, self.handle, rc, "gam_logmel_tc")
+            return mel
         rc = self.lib.gam_logmel(self.handle, wav.data_ptr(), B, N, mel.data_ptr(), self._stream())
         _lib.check(self.lib, self.handle, rc, "gam_logmel")
         return mel

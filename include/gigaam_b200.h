@@ -109,6 +109,11 @@ typedef struct gam_weights {
   const float* c1d_b1; /* f [d] */
   const void* c1d_w2;  /* h [d, k * d]        encoder.pre_encode.conv.2.weight */
   const float* c1d_b2; /* f [d] */
+  /* tensor-core front end: split-precision DFT basis h [512, 3*Kp], Kp = n_fft rounded up to 64; every 256-row tile is
+   * [128 cos rows | 128 sin rows] of bins tile*128.., K blocks [hi | hi | lo]; and the bin range of every mel filter */
+  const void* dft_w;
+  const int32_t* mel_lo; /* i32 [n_mels] first bin with a non-zero weight */
+  const int32_t* mel_hi; /* i32 [n_mels] one past the last */
 } gam_weights;
 
 int gam_create(const gam_config* cfg, const gam_weights* w, int device, gam_handle** out);
@@ -126,6 +131,13 @@ int64_t gam_workspace_bytes(const gam_handle* h, int32_t B, int64_t mel_frames);
 
 /* wav: device f32 [B, n_samples]  ->  mel: device f32 [B, n_mels, M] */
 int gam_logmel(gam_handle* h, const float* wav, int32_t B, int64_t n_samples, float* mel, void* stream);
+
+/* Same result as gam_logmel on the tensor cores: frames -> fp16 (hi, lo) split -> one K-concatenated tcgen05 GEMM
+ * against the split DFT basis with a |X|^2 epilogue -> sparse mel projection + log.  Needs scratch
+ * (gam_logmel_workspace_bytes); gam_logmel (one fused CUDA-core kernel) needs none. */
+int64_t gam_logmel_workspace_bytes(const gam_handle* h, int32_t B, int64_t n_samples);
+int gam_logmel_tc(gam_handle* h, const float* wav, int32_t B, int64_t n_samples, float* mel, void* workspace,
+                  int64_t workspace_bytes, void* stream);
 
 /* mel: device f32 [B, feat_in, M]; mel_len: device i64 [B]
  * -> enc: device f32 [B, T', d_model] (row-major; the reference's [B, d, T'] is its transpose(1,2) view)

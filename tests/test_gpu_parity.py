@@ -100,6 +100,18 @@ def test_logmel_matches_oracle(eng_ctc, v2_ctc_ckpt, B, sec, ragged):
     assert float((got - want).abs().mean()) < 1e-4
 
 
+def test_logmel_fused_cuda_core_kernel_still_matches(eng_ctc, v2_ctc_ckpt, monkeypatch):
+    """The single fused kernel (gam_logmel) and the tensor-core split-precision path (gam_logmel_tc) agree."""
+    wav, _ = synthetic.synthetic_audio(2, 3.0, seed=13, ragged=True)
+    want = orc.log_mel(wav, v2_ctc_ckpt["state_dict"], v2_ctc_ckpt["cfg"]["preprocessor"])
+    tc = eng_ctc.logmel(wav.cuda()).cpu()
+    monkeypatch.setenv("GAM_LOGMEL_FUSED", "1")
+    fused = eng_ctc.logmel(wav.cuda()).cpu()
+    for got in (tc, fused):
+        assert float((got - want).abs().max()) < 5e-3 and float((got - want).abs().mean()) < 1e-4
+    assert float((tc - fused).abs().max()) < 5e-3
+
+
 # ------------------------------------------------------------------------------------------ encoder
 @pytest.fixture(scope="session")
 def golden_ctc(golden_dir):

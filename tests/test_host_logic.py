@@ -123,6 +123,25 @@ def test_conv2_and_linear_permutations_reproduce_reference_ops():
     assert torch.allclose(y, y_ref, atol=1e-4)
 
 
+def test_split_dft_basis_reproduces_rfft_power():
+    """[f_hi | f_lo | f_hi] . [d_hi | d_hi | d_lo]^T with the tile row layout == |rfft|^2 (to ~1e-6 relative)."""
+    n = 400
+    W = engine.split_dft_basis(n).double()                         # [512, 3*448]
+    kp = W.shape[1] // 3
+    g = torch.Generator().manual_seed(0)
+    f = torch.randn(5, n, generator=g).double() * torch.hann_window(n, dtype=torch.float64)
+    fp = torch.zeros(5, kp, dtype=torch.float64)
+    fp[:, :n] = f
+    hi = fp.to(torch.float16).double()
+    lo = (fp - hi).to(torch.float16).double()
+    acc = torch.cat([hi, lo, hi], 1) @ W.t()                       # [5, 512]
+    t = acc.view(5, 2, 2, 128)                                     # tile, (cos|sin), bin
+    power = (t[:, :, 0] ** 2 + t[:, :, 1] ** 2).reshape(5, 256)[:, : n // 2 + 1]
+    want = torch.fft.rfft(f, dim=-1).abs() ** 2
+    assert float(((power - want).abs() / (want.abs() + 1e-6)).max()) < 1e-4
+    assert float((power - want).abs().max() / want.abs().max()) < 1e-6
+
+
 def test_length_arithmetic_matches_reference_formulae():
     from gigaam_b200.encoder import StridingSubsampling
     from gigaam_b200.preprocess import FeatureExtractor
