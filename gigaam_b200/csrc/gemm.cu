@@ -127,7 +127,7 @@ int launch_gemm_power(const CUtensorMap* ta, const CUtensorMap* tw, int M, int N
   p.num_k_blocks = K / kGemmBK;
   p.out = out;
   p.ldo = ldo;
-  p.scale = 1.f;
+  p.scale = 1.0f / (2048.0f * 2048.0f * 8.0f * 8.0f);   // frames x 2^11, basis x 2^3 (engine.py DFT_*_SCALE), squared
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(gemm2_f16_tn_kernel<EPI_POWER_F32, A_2D>, cudaFuncAttributeMaxDynamicSharedMemorySize, kG2Smem);

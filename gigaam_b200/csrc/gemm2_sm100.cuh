@@ -296,6 +296,7 @@ gemm2_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             o.y = __uint_as_float(va[4 * q + 1]) * __uint_as_float(va[4 * q + 1]) + __uint_as_float(vb[4 * q + 1]) * __uint_as_float(vb[4 * q + 1]);
             o.z = __uint_as_float(va[4 * q + 2]) * __uint_as_float(va[4 * q + 2]) + __uint_as_float(vb[4 * q + 2]) * __uint_as_float(vb[4 * q + 2]);
             o.w = __uint_as_float(va[4 * q + 3]) * __uint_as_float(va[4 * q + 3]) + __uint_as_float(vb[4 * q + 3]) * __uint_as_float(vb[4 * q + 3]);
+            o.x *= p.scale; o.y *= p.scale; o.z *= p.scale; o.w *= p.scale;   // undo the operand pre-scaling
             srow[q] = o;
           }
           __syncwarp();

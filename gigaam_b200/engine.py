@@ -48,6 +48,10 @@ def pack_sub_out_weight(wo: Tensor, channels: int) -> Tensor:
     return wo.reshape(wo.shape[0], channels, f2).permute(0, 2, 1).reshape(wo.shape[0], f2 * channels)
 
 
+DFT_BASIS_SCALE = 8.0      # must match kBasisScale / kFrameScale in csrc/gam_api.cu, frontend.cu
+DFT_FRAME_SCALE = 2048.0
+
+
 def split_dft_basis(n_fft: int) -> Tensor:
     """fp16 [512, 3*Kp] basis of the real DFT for the K-concatenated split-precision GEMM (Kp = n_fft rounded up to 64).
     Rows: two 256-row tiles, tile t = [128 cos rows | 128 sin rows] of bins t*128 + j (bins >= n_fft/2+1 are zero rows);
@@ -58,7 +62,9 @@ def split_dft_basis(n_fft: int) -> Tensor:
     i = torch.arange(kp, dtype=torch.float64)[None, :]
     ang = 2.0 * math.pi * k * i / n_fft
     valid = ((k < nb) & (i < n_fft)).double()
-    basis = torch.stack([torch.cos(ang) * valid, torch.sin(ang) * valid], 1)        # [256 bins, 2, kp]
+    # x 8: keeps the fp16 `lo` halves of small basis values out of the subnormal range (the frames are scaled by
+    # 2^11 for the same reason; the power epilogue multiplies by 2^-28)
+    basis = torch.stack([torch.cos(ang) * valid, torch.sin(ang) * valid], 1) * DFT_BASIS_SCALE   # [256 bins, 2, kp]
     rows = basis.view(2, 128, 2, kp).permute(0, 2, 1, 3).reshape(512, kp)          # tile, (cos|sin), bin-in-tile
     hi = rows.to(torch.float16)
     lo = (rows - hi.double()).to(torch.float16)
@@ -152,7 +158,7 @@ class Engine:
         gw.window = self._dev(window)
         gw.dft_cos = self._dev(torch.cos(ang).float())
         gw.dft_sin = self._dev(torch.sin(ang).float())
-        fb = sd["preprocessor.featurizer.0.mel_scale.fb"].float()
+        fb = sd["preprocessor.featurizer.0.mel_scale.fb"].float().cpu()
         gw.mel_fb = self._dev(fb)
         # tensor-core front end: split-precision DFT basis + bin range of every mel filter
         if K <= 256:

@@ -131,12 +131,14 @@ def test_split_dft_basis_reproduces_rfft_power():
     g = torch.Generator().manual_seed(0)
     f = torch.randn(5, n, generator=g).double() * torch.hann_window(n, dtype=torch.float64)
     fp = torch.zeros(5, kp, dtype=torch.float64)
-    fp[:, :n] = f
+    fp[:, :n] = f * 0.05 * engine.DFT_FRAME_SCALE                 # quiet signal, pre-scaled like frames_split_kernel
     hi = fp.to(torch.float16).double()
     lo = (fp - hi).to(torch.float16).double()
     acc = torch.cat([hi, lo, hi], 1) @ W.t()                       # [5, 512]
     t = acc.view(5, 2, 2, 128)                                     # tile, (cos|sin), bin
     power = (t[:, :, 0] ** 2 + t[:, :, 1] ** 2).reshape(5, 256)[:, : n // 2 + 1]
+    power = power / (engine.DFT_FRAME_SCALE * engine.DFT_BASIS_SCALE) ** 2
+    f = f * 0.05
     want = torch.fft.rfft(f, dim=-1).abs() ** 2
     assert float(((power - want).abs() / (want.abs() + 1e-6)).max()) < 1e-4
     assert float((power - want).abs().max() / want.abs().max()) < 1e-6
