@@ -165,27 +165,39 @@ __global__ void __launch_bounds__(256) subsample_conv1_kernel(const float* __res
   __syncthreads();
   const bool live = t1 < L1;
   __half* ob = out + (static_cast<size_t>(b) * T1 + t1) * F1 * C;
-  for (int c = 2 * threadIdx.x; c < C; c += 2 * blockDim.x) {  // channel pair -> half2 stores
-    float w0[9], w1[9];
+  // thread = 8 consecutive channels x half of the f1 range: one 16-byte store per (f1, thread), 512 contiguous bytes
+  // per warp instruction -- the kernel is bound by the 1.5 GB it writes, not by its 9 MACs per output
+  const int groups = C / 8;
+  const int cg = threadIdx.x % groups, fh = threadIdx.x / groups;
+  const int nfh = blockDim.x / groups;
+  if (fh >= nfh) return;
+  const int c = cg * 8;
+  float wk[8][9], bb[8];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) {
-      w0[k] = __ldg(w + c * 9 + k);
-      w1[k] = __ldg(w + (c + 1) * 9 + k);
+  for (int i = 0; i < 8; ++i) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) wk[i][k] = __ldg(w + (c + i) * 9 + k);
+    bb[i] = __ldg(bias + c + i);
+  }
+  for (int f1 = fh; f1 < F1; f1 += nfh) {
+    float x[9];
+#pragma unroll
+    for (int kt = 0; kt < 3; ++kt)
+#pragma unroll
+      for (int kf = 0; kf < 3; ++kf) x[kt * 3 + kf] = patch[kt][2 * f1 + kf];
+    uint32_t pk[4];
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) {
+      float a0 = bb[i], a1 = bb[i + 1];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        a0 = fmaf(wk[i][k], x[k], a0);
+        a1 = fmaf(wk[i + 1][k], x[k], a1);
+      }
+      __half2 hh = live ? __floats2half2_rn(fmaxf(a0, 0.f), fmaxf(a1, 0.f)) : __floats2half2_rn(0.f, 0.f);
+      pk[i >> 1] = *reinterpret_cast<uint32_t*>(&hh);
     }
-    const float b0 = __ldg(bias + c), b1 = __ldg(bias + c + 1);
-    for (int f1 = 0; f1 < F1; ++f1) {
-      float a0 = b0, a1 = b1;
-#pragma unroll
-      for (int kt = 0; kt < 3; ++kt)
-#pragma unroll
-        for (int kf = 0; kf < 3; ++kf) {
-          const float x = patch[kt][2 * f1 + kf];
-          a0 = fmaf(w0[kt * 3 + kf], x, a0);
-          a1 = fmaf(w1[kt * 3 + kf], x, a1);
-        }
-      *reinterpret_cast<__half2*>(ob + static_cast<size_t>(f1) * C + c) =
-          live ? __floats2half2_rn(fmaxf(a0, 0.f), fmaxf(a1, 0.f)) : __floats2half2_rn(0.f, 0.f);
-    }
+    *reinterpret_cast<uint4*>(ob + static_cast<size_t>(f1) * C + c) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
   }
 }
 
@@ -332,9 +344,9 @@ int launch_logmel(const float* wav, int B, int n_samples, int n_frames, const fl
 
 int launch_subsample_conv1(const float* mel, const int* len0, const int* len1, const float* w, const float* bias,
                            __half* out, int B, int M, int F, int T1, int F1, int C, cudaStream_t s) {
-  if (F > 70) return -1;
+  if (F > 70 || C % 8 != 0 || C / 8 > 128) return -1;
   dim3 grid(T1, B);
-  subsample_conv1_kernel<<<grid, 256, 0, s>>>(mel, len0, len1, w, bias, out, M, F, T1, F1, C);
+  subsample_conv1_kernel<<<grid, 2 * (C / 8), 0, s>>>(mel, len0, len1, w, bias, out, M, F, T1, F1, C);
   return 0;
 }
 

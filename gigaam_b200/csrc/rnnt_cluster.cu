@@ -20,7 +20,8 @@ namespace gam {
 namespace {
 
 constexpr int kCl = 16;           // CTAs per cluster
-constexpr int kNU = 8;            // utterances decoded in lock-step per cluster
+constexpr int kNU = 4;            // utterances decoded in lock-step per cluster
+constexpr int kWoRows = 8;        // class rows of W_o kept in smem per CTA (covers V+1 <= 128)
 constexpr int kH = 320;
 constexpr int kHS = kH / kCl;     // hidden units owned per CTA (20)
 constexpr int kThreads = 512;
@@ -55,6 +56,12 @@ struct Smem {
   int best_i[2][kNU][kCl];
   float wbest_v[kThreads / 32][kNU];
   int wbest_i[kThreads / 32][kNU];
+  // cluster.sync() invalidates L1, so everything a round needs from global memory is staged here once per round,
+  // right after the decision, with a single exposed L2 latency
+  float ep[kNU][kH];              // encoder projection row of the utterance's current frame
+  float eg[kNU][4 * kHS];         // own gate rows of emb_gates[label]
+  float wo[kWoRows][kPitch];      // own class rows of W_o (small vocabularies only)
+  float bo[kWoRows];
 };
 
 __device__ __forceinline__ float sigm(float x) { return 1.0f / (1.0f + expf(-x)); }
@@ -82,6 +89,12 @@ __global__ void __launch_bounds__(kThreads, 1) rnnt_cluster_kernel(const RnntClP
   const int cls_per = (p.V1 + kCl - 1) / kCl;
   const int cls0 = rank * cls_per;
   const int cls1 = min(p.V1, cls0 + cls_per);
+  const bool wo_smem = cls_per <= kWoRows;
+  if (wo_smem) {
+    for (int i = tid; i < (cls1 - cls0) * kH; i += kThreads) s.wo[i / kH][i % kH] = __ldg(p.wo + static_cast<size_t>(cls0 + i / kH) * kH + i % kH);
+    for (int i = tid; i < cls1 - cls0; i += kThreads) s.bo[i] = __ldg(p.bo + cls0 + i);
+  }
+  __syncthreads();
 
   for (int group = cluster_id; group < p.num_groups; group += num_clusters) {
     // ---- per-utterance control state: identical in every thread of every CTA of the cluster
@@ -96,6 +109,15 @@ __global__ void __launch_bounds__(kThreads, 1) rnnt_cluster_kernel(const RnntClP
     }
     for (int i = tid; i < kNU * kH; i += kThreads) (&s.h[0][0])[i] = 0.f;
     for (int i = tid; i < kNU * kHS; i += kThreads) (&s.c[0][0])[i] = 0.f;
+    for (int d = tid; d < kNU * kH; d += kThreads) {
+      const int u = d / kH, j = d % kH;
+      const int ug = group * p.nu + u;
+      s.ep[u][j] = L[u] > 0 ? __ldg(p.encproj + static_cast<size_t>(ug) * p.T * kH + j) : 0.f;
+    }
+    for (int d = tid; d < kNU * 4 * kHS; d += kThreads) {
+      const int r = d % (4 * kHS);
+      s.eg[d / (4 * kHS)][r] = __ldg(p.emb_gates + static_cast<size_t>(p.blank) * G + (r / kHS) * kH + rank * kHS + r % kHS);
+    }
     cluster.sync();
     int round = 0;
 
@@ -126,7 +148,8 @@ __global__ void __launch_bounds__(kThreads, 1) rnnt_cluster_kernel(const RnntClP
             a2 = fmaf(w[k + 2], hv[k + 2], a2);
             a3 = fmaf(w[k + 3], hv[k + 3], a3);
           }
-          s.gates[u][r] = __ldg(p.emb_gates + static_cast<size_t>(label[u]) * G + g * kH + rank * kHS + j) + ((a0 + a1) + (a2 + a3));
+          (void)g; (void)j;
+          s.gates[u][r] = s.eg[u][r] + ((a0 + a1) + (a2 + a3));
         }
         __syncthreads();
         for (int d = tid; d < kNU * kHS; d += kThreads) {
@@ -167,7 +190,8 @@ __global__ void __launch_bounds__(kThreads, 1) rnnt_cluster_kernel(const RnntClP
         const int u = d / kH, j = d % kH;
         const int ug = group * p.nu + u;
         float v = 0.f;
-        if (t_u[u] < L[u]) v = fmaxf(__ldg(p.encproj + (static_cast<size_t>(ug) * p.T + t_u[u]) * kH + j) + s.pg[u][j], 0.f);
+        (void)ug;
+        if (t_u[u] < L[u]) v = fmaxf(s.ep[u][j] + s.pg[u][j], 0.f);
         s.hid[u][j] = v;
       }
       __syncthreads();
@@ -176,16 +200,16 @@ __global__ void __launch_bounds__(kThreads, 1) rnnt_cluster_kernel(const RnntClP
 #pragma unroll
       for (int u = 0; u < kNU; ++u) { bv[u] = -INFINITY; bi[u] = 0x7fffffff; }
       for (int cls = cls0 + warp; cls < cls1; cls += kThreads / 32) {
-        const float* w = p.wo + static_cast<size_t>(cls) * kH;
+        const float* w = wo_smem ? s.wo[cls - cls0] : p.wo + static_cast<size_t>(cls) * kH;
         float acc[kNU];
 #pragma unroll
         for (int u = 0; u < kNU; ++u) acc[u] = 0.f;
         for (int k = lane; k < kH; k += 32) {
-          const float wv = __ldg(w + k);
+          const float wv = w[k];
 #pragma unroll
           for (int u = 0; u < kNU; ++u) acc[u] = fmaf(wv, s.hid[u][k], acc[u]);
         }
-        const float bo = __ldg(p.bo + cls);
+        const float bo = wo_smem ? s.bo[cls - cls0] : __ldg(p.bo + cls);
 #pragma unroll
         for (int u = 0; u < kNU; ++u) {
           float a = acc[u];
@@ -253,6 +277,16 @@ __global__ void __launch_bounds__(kThreads, 1) rnnt_cluster_kernel(const RnntClP
       for (int d = tid; d < kNU * kHS; d += kThreads) {
         const int u = d / kHS;
         if (need_lstm[u]) s.c[u][d % kHS] = s.cn[u][d % kHS];
+      }
+      // stage what the next round needs from global memory (one exposed L2 round trip per round)
+      for (int d = tid; d < kNU * kH; d += kThreads) {
+        const int u = d / kH, j = d % kH;
+        if (t_u[u] < L[u]) s.ep[u][j] = __ldg(p.encproj + (static_cast<size_t>(group * p.nu + u) * p.T + t_u[u]) * kH + j);
+      }
+      for (int d = tid; d < kNU * 4 * kHS; d += kThreads) {
+        const int u = d / (4 * kHS), r = d % (4 * kHS);
+        if (need_lstm[u] && t_u[u] < L[u])
+          s.eg[u][r] = __ldg(p.emb_gates + static_cast<size_t>(label[u]) * G + (r / kHS) * kH + rank * kHS + r % kHS);
       }
       __syncthreads();
     }
