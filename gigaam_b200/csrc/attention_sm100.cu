@@ -558,41 +558,62 @@ __global__ void __launch_bounds__(64 + 256, 1) attention_persistent_kernel(const
       const int nchunks = (klen + 31) >> 5;
       ptx::mbar_wait(&s_full[qt], ipar);
       ptx::tc_fence_after();
+      // Both sweeps are software-pipelined over two register buffers: the TMEM load of chunk c+1 is in flight while
+      // chunk c is reduced / exponentiated (tcgen05.wait::ld waits for every outstanding load, so the next load is
+      // issued right after the wait and before the math).
       float m = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < nchunks; ++c) {
-        uint32_t v[32];
-        ptx::tmem_ld_32x32b_x32(t_s + c * 32, v);
-        ptx::tmem_ld_wait();
+      uint32_t va[32], vb[32];
+      auto row_max = [&](const uint32_t* v, int c) {
 #pragma unroll
         for (int j = 0; j < 32; ++j)
           if (c * 32 + j < klen) m = fmaxf(m, __uint_as_float(v[j]));
+      };
+      if (nchunks > 0) ptx::tmem_ld_32x32b_x32(t_s, va);
+#pragma unroll 1
+      for (int c = 0; c < nchunks; c += 2) {
+        ptx::tmem_ld_wait();
+        if (c + 1 < nchunks) ptx::tmem_ld_32x32b_x32(t_s + (c + 1) * 32, vb);
+        row_max(va, c);
+        if (c + 1 < nchunks) {
+          ptx::tmem_ld_wait();
+          if (c + 2 < nchunks) ptx::tmem_ld_32x32b_x32(t_s + (c + 2) * 32, va);
+          row_max(vb, c + 1);
+        }
       }
       if (m == -INFINITY) m = 0.f;
       const float mc = m * p.scale_log2;
       float sum = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < nkb * 4; ++c) {
+      // P chunk c (32 keys = 16 packed fp16 columns) overwrites columns [16c, 16c+16) of this row: part of S chunk c/2,
+      // already consumed, and below every chunk whose load may still be in flight
+      auto exp_store = [&](const uint32_t* v, int c) {
         uint32_t pk[16];
-        if (c < nchunks) {
-          uint32_t v[32];
-          ptx::tmem_ld_32x32b_x32(t_s + c * 32, v);
-          ptx::tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            const float p0 = (c * 32 + j < klen) ? ex2(fmaf(__uint_as_float(v[j]), p.scale_log2, -mc)) : 0.f;
-            const float p1 = (c * 32 + j + 1 < klen) ? ex2(fmaf(__uint_as_float(v[j + 1]), p.scale_log2, -mc)) : 0.f;
-            sum += p0 + p1;
-            __half2 hh = __floats2half2_rn(p0, p1);
-            pk[j >> 1] = *reinterpret_cast<uint32_t*>(&hh);
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) pk[j] = 0u;
+        for (int j = 0; j < 32; j += 2) {
+          const float p0 = (c * 32 + j < klen) ? ex2(fmaf(__uint_as_float(v[j]), p.scale_log2, -mc)) : 0.f;
+          const float p1 = (c * 32 + j + 1 < klen) ? ex2(fmaf(__uint_as_float(v[j + 1]), p.scale_log2, -mc)) : 0.f;
+          sum += p0 + p1;
+          __half2 hh = __floats2half2_rn(p0, p1);
+          pk[j >> 1] = *reinterpret_cast<uint32_t*>(&hh);
         }
-        // P chunk c (32 keys = 16 packed columns) overwrites columns [16c, 16c+16) of this row: part of S chunk c/2,
-        // already consumed
         ptx::tmem_st_32x32b_x16(t_s + c * 16, pk);
+      };
+      if (nchunks > 0) ptx::tmem_ld_32x32b_x32(t_s, va);
+#pragma unroll 1
+      for (int c = 0; c < nchunks; c += 2) {
+        ptx::tmem_ld_wait();
+        if (c + 1 < nchunks) ptx::tmem_ld_32x32b_x32(t_s + (c + 1) * 32, vb);
+        exp_store(va, c);
+        if (c + 1 < nchunks) {
+          ptx::tmem_ld_wait();
+          if (c + 2 < nchunks) ptx::tmem_ld_32x32b_x32(t_s + (c + 2) * 32, va);
+          exp_store(vb, c + 1);
+        }
+      }
+      {
+        uint32_t zero[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) zero[j] = 0u;
+        for (int c = nchunks; c < nkb * 4; ++c) ptx::tmem_st_32x32b_x16(t_s + c * 16, zero);
       }
       ptx::tmem_st_wait();
       ptx::tc_fence_before();

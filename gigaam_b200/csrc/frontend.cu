@@ -152,25 +152,23 @@ __global__ void __launch_bounds__(256) subsample_conv1_kernel(const float* __res
                                                               const int* __restrict__ len1, const float* __restrict__ w,
                                                               const float* __restrict__ bias, __half* __restrict__ out,
                                                               int M, int F, int T1, int F1, int C) {
-  __shared__ float patch[3][72];  // rows 2t1-1..2t1+1, features -1..F  (F <= 70)
-  const int t1 = blockIdx.x, b = blockIdx.y;
+  constexpr int kTT = 8;                      // output time steps per block (weights stay in registers across them)
+  __shared__ float patch[2 * kTT + 1][72];    // mel rows 2 t1_0 - 1 .. 2 t1_0 + 2 kTT - 1, features -1..F  (F <= 70)
+  const int t1_0 = blockIdx.x * kTT, b = blockIdx.y;
   const int L0 = len0[b], L1 = len1[b];
-  for (int i = threadIdx.x; i < 3 * (F + 2); i += blockDim.x) {
-    const int kt = i / (F + 2), ff = i % (F + 2) - 1;
-    const int t0 = 2 * t1 + kt - 1;
+  for (int i = threadIdx.x; i < (2 * kTT + 1) * (F + 2); i += blockDim.x) {
+    const int rr = i / (F + 2), ff = i % (F + 2) - 1;
+    const int t0 = 2 * t1_0 + rr - 1;
     float v = 0.f;
     if (t0 >= 0 && t0 < M && t0 < L0 && ff >= 0 && ff < F) v = mel[(static_cast<size_t>(b) * F + ff) * M + t0];
-    patch[kt][ff + 1] = v;
+    patch[rr][ff + 1] = v;
   }
   __syncthreads();
-  const bool live = t1 < L1;
-  __half* ob = out + (static_cast<size_t>(b) * T1 + t1) * F1 * C;
-  // thread = 8 consecutive channels x half of the f1 range: one 16-byte store per (f1, thread), 512 contiguous bytes
-  // per warp instruction -- the kernel is bound by the 1.5 GB it writes, not by its 9 MACs per output
+  // thread = 8 consecutive channels x half of the f1 range: one 16-byte store per (t1, f1, thread), 512 contiguous
+  // bytes per warp instruction -- the kernel is bound by the 1.5 GB it writes, not by its 9 MACs per output
   const int groups = C / 8;
   const int cg = threadIdx.x % groups, fh = threadIdx.x / groups;
   const int nfh = blockDim.x / groups;
-  if (fh >= nfh) return;
   const int c = cg * 8;
   float wk[8][9], bb[8];
 #pragma unroll
@@ -179,25 +177,31 @@ __global__ void __launch_bounds__(256) subsample_conv1_kernel(const float* __res
     for (int k = 0; k < 9; ++k) wk[i][k] = __ldg(w + (c + i) * 9 + k);
     bb[i] = __ldg(bias + c + i);
   }
-  for (int f1 = fh; f1 < F1; f1 += nfh) {
-    float x[9];
+  for (int tt = 0; tt < kTT; ++tt) {
+    const int t1 = t1_0 + tt;
+    if (t1 >= T1) break;
+    const bool live = t1 < L1;
+    __half* ob = out + (static_cast<size_t>(b) * T1 + t1) * F1 * C;
+    for (int f1 = fh; f1 < F1; f1 += nfh) {
+      float x[9];
 #pragma unroll
-    for (int kt = 0; kt < 3; ++kt)
+      for (int kt = 0; kt < 3; ++kt)
 #pragma unroll
-      for (int kf = 0; kf < 3; ++kf) x[kt * 3 + kf] = patch[kt][2 * f1 + kf];
-    uint32_t pk[4];
+        for (int kf = 0; kf < 3; ++kf) x[kt * 3 + kf] = patch[2 * tt + kt][2 * f1 + kf];
+      uint32_t pk[4];
 #pragma unroll
-    for (int i = 0; i < 8; i += 2) {
-      float a0 = bb[i], a1 = bb[i + 1];
+      for (int i = 0; i < 8; i += 2) {
+        float a0 = bb[i], a1 = bb[i + 1];
 #pragma unroll
-      for (int k = 0; k < 9; ++k) {
-        a0 = fmaf(wk[i][k], x[k], a0);
-        a1 = fmaf(wk[i + 1][k], x[k], a1);
+        for (int k = 0; k < 9; ++k) {
+          a0 = fmaf(wk[i][k], x[k], a0);
+          a1 = fmaf(wk[i + 1][k], x[k], a1);
+        }
+        __half2 hh = live ? __floats2half2_rn(fmaxf(a0, 0.f), fmaxf(a1, 0.f)) : __floats2half2_rn(0.f, 0.f);
+        pk[i >> 1] = *reinterpret_cast<uint32_t*>(&hh);
       }
-      __half2 hh = live ? __floats2half2_rn(fmaxf(a0, 0.f), fmaxf(a1, 0.f)) : __floats2half2_rn(0.f, 0.f);
-      pk[i >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+      *reinterpret_cast<uint4*>(ob + static_cast<size_t>(f1) * C + c) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }
-    *reinterpret_cast<uint4*>(ob + static_cast<size_t>(f1) * C + c) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
   }
 }
 
@@ -345,7 +349,7 @@ int launch_logmel(const float* wav, int B, int n_samples, int n_frames, const fl
 int launch_subsample_conv1(const float* mel, const int* len0, const int* len1, const float* w, const float* bias,
                            __half* out, int B, int M, int F, int T1, int F1, int C, cudaStream_t s) {
   if (F > 70 || C % 8 != 0 || C / 8 > 128) return -1;
-  dim3 grid(T1, B);
+  dim3 grid((T1 + 7) / 8, B);
   subsample_conv1_kernel<<<grid, 2 * (C / 8), 0, s>>>(mel, len0, len1, w, bias, out, M, F, T1, F1, C);
   return 0;
 }
