@@ -563,10 +563,25 @@ __global__ void __launch_bounds__(64 + 256, 1) attention_persistent_kernel(const
       // issued right after the wait and before the math).
       float m = -INFINITY;
       uint32_t va[32], vb[32];
+      // only the chunk that straddles klen pays for per-key predicates (the softmax is issue-bound: ~10 instructions
+      // per score before this split)
+      const int full_chunks = klen >> 5;
       auto row_max = [&](const uint32_t* v, int c) {
+        if (c < full_chunks) {
+          float m0 = m, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (c * 32 + j < klen) m = fmaxf(m, __uint_as_float(v[j]));
+          for (int j = 0; j < 32; j += 4) {
+            m0 = fmaxf(m0, __uint_as_float(v[j]));
+            m1 = fmaxf(m1, __uint_as_float(v[j + 1]));
+            m2 = fmaxf(m2, __uint_as_float(v[j + 2]));
+            m3 = fmaxf(m3, __uint_as_float(v[j + 3]));
+          }
+          m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (c * 32 + j < klen) m = fmaxf(m, __uint_as_float(v[j]));
+        }
       };
       if (nchunks > 0) ptx::tmem_ld_32x32b_x32(t_s, va);
 #pragma unroll 1
@@ -585,15 +600,29 @@ __global__ void __launch_bounds__(64 + 256, 1) attention_persistent_kernel(const
       float sum = 0.f;
       // P chunk c (32 keys = 16 packed fp16 columns) overwrites columns [16c, 16c+16) of this row: part of S chunk c/2,
       // already consumed, and below every chunk whose load may still be in flight
+      float sum1 = 0.f;
       auto exp_store = [&](const uint32_t* v, int c) {
         uint32_t pk[16];
+        if (c < full_chunks) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          const float p0 = (c * 32 + j < klen) ? ex2(fmaf(__uint_as_float(v[j]), p.scale_log2, -mc)) : 0.f;
-          const float p1 = (c * 32 + j + 1 < klen) ? ex2(fmaf(__uint_as_float(v[j + 1]), p.scale_log2, -mc)) : 0.f;
-          sum += p0 + p1;
-          __half2 hh = __floats2half2_rn(p0, p1);
-          pk[j >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+          for (int j = 0; j < 32; j += 2) {
+            const float p0 = ex2(fmaf(__uint_as_float(v[j]), p.scale_log2, -mc));
+            const float p1 = ex2(fmaf(__uint_as_float(v[j + 1]), p.scale_log2, -mc));
+            sum += p0;
+            sum1 += p1;
+            __half2 hh = __floats2half2_rn(p0, p1);
+            pk[j >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const float p0 = (c * 32 + j < klen) ? ex2(fmaf(__uint_as_float(v[j]), p.scale_log2, -mc)) : 0.f;
+            const float p1 = (c * 32 + j + 1 < klen) ? ex2(fmaf(__uint_as_float(v[j + 1]), p.scale_log2, -mc)) : 0.f;
+            sum += p0;
+            sum1 += p1;
+            __half2 hh = __floats2half2_rn(p0, p1);
+            pk[j >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+          }
         }
         ptx::tmem_st_32x32b_x16(t_s + c * 16, pk);
       };
@@ -629,6 +658,7 @@ __global__ void __launch_bounds__(64 + 256, 1) attention_persistent_kernel(const
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&o_empty[qt]);   // region free for the next item's S
+      sum += sum1;
       const float inv = sum > 0.f ? 1.0f / sum : 0.f;
       const int q = qt * 128 + r;
       if (q < p.T) {
