@@ -439,7 +439,7 @@ struct AttnPersParams {
   float scale_log2;
 };
 
-__global__ void __launch_bounds__(64 + 256, 1) attention_persistent_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
+__global__ void __launch_bounds__(128 + 256, 1) attention_persistent_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
                                                                           const AttnPersParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -462,7 +462,7 @@ __global__ void __launch_bounds__(64 + 256, 1) attention_persistent_kernel(const
     ptx::prefetch_tmap(&tmap_qkv);
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&kv_full[i], 1);
-      ptx::mbar_init(&kv_empty[i], 1);
+      ptx::mbar_init(&kv_empty[i], p.nkb);   // one commit per query-tile stream
       ptx::mbar_init(&s_full[i], 1);
       ptx::mbar_init(&p_full[i], 4);
       ptx::mbar_init(&o_full[i], 1);
@@ -470,7 +470,7 @@ __global__ void __launch_bounds__(64 + 256, 1) attention_persistent_kernel(const
     }
     ptx::fence_mbar_init();
   }
-  if (warp_idx == 1) ptx::tmem_alloc<512>(tmem_slot);
+  if (warp_idx == 3) ptx::tmem_alloc<512>(tmem_slot);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -497,20 +497,22 @@ __global__ void __launch_bounds__(64 + 256, 1) attention_persistent_kernel(const
         }
       }
     }
-  } else if (warp_idx == 1) {
-    // ===================================================== MMA issuer
-    constexpr uint32_t kIdescS = ptx::make_idesc_f16(128, 128, 0, 0);
-    constexpr uint32_t kIdescPV = ptx::make_idesc_f16(128, 64, 0, 1);   // B (= V) MN-major; A (= P) from TMEM
-    const int ksteps_qk = p.dk / 16;
-    int it = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-      const int buf = it & 1;
-      const uint32_t ipar = it & 1;
-      uint8_t* sQ = smem + buf * item_bytes;
-      uint8_t* sK = sQ + nkb * kTileBytes;
-      uint8_t* sV = sK + nkb * kTileBytes;
-      ptx::mbar_wait(&kv_full[buf], (it >> 1) & 1);
-      for (int qt = 0; qt < nkb; ++qt) {
+  } else if (warp_idx == 1 || warp_idx == 2) {
+    // ===================================================== MMA issuers: one per query-tile stream, so the two streams
+    // drift apart and fill each other's hand-off bubbles (S -> softmax -> P.V -> O read is a serial chain per tile)
+    const int qt = warp_idx - 1;
+    if (qt < nkb) {
+      constexpr uint32_t kIdescS = ptx::make_idesc_f16(128, 128, 0, 0);
+      constexpr uint32_t kIdescPV = ptx::make_idesc_f16(128, 64, 0, 1);   // B (= V) MN-major; A (= P) from TMEM
+      const int ksteps_qk = p.dk / 16;
+      int it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const uint32_t ipar = it & 1;
+        uint8_t* sQ = smem + buf * item_bytes;
+        uint8_t* sK = sQ + nkb * kTileBytes;
+        uint8_t* sV = sK + nkb * kTileBytes;
+        ptx::mbar_wait(&kv_full[buf], (it >> 1) & 1);
         ptx::mbar_wait(&o_empty[qt], ipar ^ 1);   // previous item's O has been read out of this tile's region
         ptx::tc_fence_after();
         if (ptx::elect_one()) {
@@ -524,8 +526,6 @@ __global__ void __launch_bounds__(64 + 256, 1) attention_persistent_kernel(const
           ptx::mma_commit(&s_full[qt]);
         }
         __syncwarp();
-      }
-      for (int qt = 0; qt < nkb; ++qt) {
         ptx::mbar_wait(&p_full[qt], ipar);
         ptx::tc_fence_after();
         if (ptx::elect_one()) {
@@ -537,14 +537,14 @@ __global__ void __launch_bounds__(64 + 256, 1) attention_persistent_kernel(const
                               ptx::make_smem_desc_sw128(va + ks * 2048, 1024, 1024), kIdescPV, (kb | ks) != 0 ? 1u : 0u);
           }
           ptx::mma_commit(&o_full[qt]);
-          if (qt == nkb - 1) ptx::mma_commit(&kv_empty[buf]);   // every MMA that reads this ring slot has retired
+          ptx::mma_commit(&kv_empty[buf]);   // this stream is done with the ring slot (count = nkb streams)
         }
         __syncwarp();
       }
     }
-  } else if (warp_idx < 2 + 4 * nkb) {
+  } else if (warp_idx >= 4 && warp_idx < 4 + 4 * nkb) {
     // ===================================================== softmax + output (one warpgroup per query tile)
-    const int qt = (warp_idx - 2) >> 2;
+    const int qt = (warp_idx - 4) >> 2;
     const int quad = warp_idx & 3;
     const int lane = threadIdx.x & 31;
     const int r = quad * 32 + lane;
@@ -681,7 +681,7 @@ __global__ void __launch_bounds__(64 + 256, 1) attention_persistent_kernel(const
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp_idx == 1) {
+  if (warp_idx == 3) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc<512>(tmem_base);
   }
@@ -957,7 +957,7 @@ static int launch_attention_persistent(const CUtensorMap* tmap_qkv, const int* k
   const int items = B * H;
   const int grid = items < num_sms ? items : num_sms;
   const int smem = 2 * 3 * p.nkb * kTileBytes + 256 + 1024;
-  attention_persistent_kernel<<<grid, 64 + 128 * p.nkb, smem, s>>>(*tmap_qkv, p);
+  attention_persistent_kernel<<<grid, 128 + 128 * p.nkb, smem, s>>>(*tmap_qkv, p);
   return 0;
 }
 static int attention_res_smem_bytes(int nkb, int QT) { return (QT + 2 * nkb + QT * 2 * nkb) * kTileBytes + 128 + 1024; }
