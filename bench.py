@@ -63,7 +63,7 @@ class ClockSampler:
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -71,16 +71,21 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
-    def stop(self) -> dict:
+    def stop(self, t0: float = None, t1: float = None) -> dict:
+        """Summary of the samples received inside [t0, t1] (the timed region); the sampler itself is started before the
+        warm-up so that nvidia-smi's start-up latency does not eat the window."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
+        inside = [ln for ts, ln in self.lines if t0 is None or (t0 <= ts <= t1 + 0.03)]
+        if not inside:
+            inside = [ln for _, ln in self.lines[-3:]]
         sm, smax, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 8:
                 continue
@@ -234,25 +239,27 @@ def main():
         graph.replay()
         gather(g_ids, g_counts)
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for i in range(max(args.warmup, 3)):
         graph_step(i)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_begin = time.perf_counter()
     e0.record()
     for i in range(args.steps):
         graph_step(i)
     e1.record()
     torch.cuda.synchronize()
+    t_end = time.perf_counter()
     if world > 1:
         dist.barrier()
     ms_total = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -313,8 +320,12 @@ def main():
         avg_ms = ms_sum / n
         fpl = cls_flops.get(name)
         achieved = fpl / (avg_ms * 1e-3) / 1e12 if fpl else None
+        traffic = None
+        tr = ROOT / "profiles" / "ncu_traffic.json"   # dram bytes per launch from the committed ncu --set full capture
+        if tr.exists():
+            traffic = json.loads(tr.read_text()).get(name)
         roofline = {"kernel": name, "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                    "frac": (achieved / peak_tf) if achieved else None, "traffic": None, "peak_source": peak_src,
+                    "frac": (achieved / peak_tf) if achieved else None, "traffic": traffic, "peak_source": peak_src,
                     "avg_launch_ms": avg_ms, "launches_per_step": n // nprof, "share_of_step": ms_sum / total_ms,
                     "flops_per_launch": fpl,
                     "step_tflops": B * fl["total"] / (ms_per_step * 1e-3) / 1e12,
