@@ -16,6 +16,7 @@
 //               pass 1 = row max, pass 2 = exp2 / row sum / P -> smem.  S is recomputed in pass 2
 //               (tensor time is negligible here) so O never needs rescaling.
 #include "kernels.h"
+#include "launch.cuh"
 #include "ptx.cuh"
 
 namespace gam {
@@ -443,6 +444,7 @@ __global__ void __launch_bounds__(128 + 256, 1) attention_persistent_kernel(cons
                                                                           const AttnPersParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  ptx::pdl_launch_dependents();
   const int nkb = p.nkb;                    // 1 or 2: key blocks == query tiles
   const int item_bytes = 3 * nkb * kTileBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * item_bytes);
@@ -475,6 +477,7 @@ __global__ void __launch_bounds__(128 + 256, 1) attention_persistent_kernel(cons
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  ptx::pdl_wait();   // PDL: the set-up above overlapped the QKV GEMM's tail
 
   if (warp_idx == 0) {
     // ===================================================== TMA producer
@@ -957,8 +960,7 @@ static int launch_attention_persistent(const CUtensorMap* tmap_qkv, const int* k
   const int items = B * H;
   const int grid = items < num_sms ? items : num_sms;
   const int smem = 2 * 3 * p.nkb * kTileBytes + 256 + 1024;
-  attention_persistent_kernel<<<grid, 128 + 128 * p.nkb, smem, s>>>(*tmap_qkv, p);
-  return 0;
+  return launch_pdl(attention_persistent_kernel, dim3(grid), dim3(128 + 128 * p.nkb), smem, s, *tmap_qkv, p) == cudaSuccess ? 0 : -2;
 }
 static int attention_res_smem_bytes(int nkb, int QT) { return (QT + 2 * nkb + QT * 2 * nkb) * kTileBytes + 128 + 1024; }
 

@@ -4,6 +4,7 @@
 
 #include "gemm2_sm100.cuh"
 #include "kernels.h"
+#include "launch.cuh"
 
 namespace gam {
 namespace {
@@ -38,8 +39,7 @@ int launch_v2(const CUtensorMap* ta, const CUtensorMap* tw, GemmParams p, int nu
   const int max_pairs = num_sms / 2;
   const int npairs = tiles < max_pairs ? tiles : max_pairs;
   if (npairs <= 0) return 0;
-  kern<<<2 * npairs, kG2Threads, kG2Smem, s>>>(*ta, *tw, p);
-  return cudaPeekAtLastError() == cudaSuccess ? 0 : -2;
+  return launch_pdl(kern, dim3(2 * npairs), dim3(kG2Threads), kG2Smem, s, *ta, *tw, p) == cudaSuccess ? 0 : -2;
 }
 
 template <int EPI, int AMODE>

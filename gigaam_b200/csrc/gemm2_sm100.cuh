@@ -55,6 +55,7 @@ gemm2_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   uint64_t* tmem_empty = tmem_full + 2;           // [2]  (leader's copy is the live one)
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
+  ptx::pdl_launch_dependents();
   const int warp_idx = threadIdx.x >> 5;
   const uint32_t rank = ptx::cluster_ctarank();
   const bool leader = rank == 0;
@@ -80,6 +81,8 @@ gemm2_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   ptx::cluster_sync();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
+  // everything above overlapped the previous kernel's tail (PDL); from here on we touch its outputs
+  ptx::pdl_wait();
 
   if (warp_idx == 0) {
     // ===================================================== TMA producer (both CTAs)
