@@ -10,8 +10,10 @@ namespace gam {
 inline bool pdl_enabled() {
   static int v = -1;
   if (v < 0) {
+    // measured on c2 (64 x 10 s, CUDA graph): 12.30 ms with PDL vs 12.15 ms without -- the persistent kernels
+    // own their SM (200+ KB smem), so dependents cannot become resident early; opt-in only (GAM_PDL=1)
     const char* e = std::getenv("GAM_PDL");
-    v = (e && e[0] == '0') ? 0 : 1;
+    v = (e && e[0] == '1') ? 1 : 0;
   }
   return v == 1;
 }

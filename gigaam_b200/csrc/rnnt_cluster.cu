@@ -100,12 +100,18 @@ __global__ void __launch_bounds__(kThreads, 1) rnnt_cluster_kernel(const RnntClP
     // ---- per-utterance control state: identical in every thread of every CTA of the cluster
     int t_u[kNU], nsym[kNU], cnt[kNU], label[kNU], L[kNU];
     bool need_lstm[kNU];
+    // hb[u]: which of the two hn buffers holds utterance u's CURRENT candidate state.  A candidate may be consumed
+    // many rounds after it was computed (blank frames in between), so the buffer is chosen per utterance, not per
+    // round; the next LSTM of u writes the other buffer, which keeps remote writes of round r+1 away from the
+    // commit reads of round r.
+    int hb[kNU];
 #pragma unroll
     for (int u = 0; u < kNU; ++u) {
       const int ug = group * p.nu + u;
       L[u] = (u < p.nu && ug < p.B) ? min(max(p.len[ug], 0), p.T) : 0;
       t_u[u] = 0; nsym[u] = 0; cnt[u] = 0; label[u] = p.blank;
       need_lstm[u] = L[u] > 0;
+      hb[u] = 0;
     }
     for (int i = tid; i < kNU * kH; i += kThreads) (&s.h[0][0])[i] = 0.f;
     for (int i = tid; i < kNU * kHS; i += kThreads) (&s.c[0][0])[i] = 0.f;
@@ -161,7 +167,7 @@ __global__ void __launch_bounds__(kThreads, 1) rnnt_cluster_kernel(const RnntClP
           s.cn[u][j] = cn;
           const float hn = og * tanhf(cn);
 #pragma unroll
-          for (int rr = 0; rr < kCl; ++rr) cluster.map_shared_rank(&s.hn[par][u][rank * kHS + j], rr)[0] = hn;
+          for (int rr = 0; rr < kCl; ++rr) cluster.map_shared_rank(&s.hn[hb[u] ^ 1][u][rank * kHS + j], rr)[0] = hn;
         }
         cluster.sync();
         // ---------------- prediction projection: own rows of W_p
@@ -169,7 +175,7 @@ __global__ void __launch_bounds__(kThreads, 1) rnnt_cluster_kernel(const RnntClP
           const int u = d / kHS, j = d % kHS;
           if (!(need_lstm[u] && t_u[u] < L[u])) continue;
           const float* w = s.wp[j];
-          const float* hv = s.hn[par][u];
+          const float* hv = s.hn[hb[u] ^ 1][u];
           float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll 8
           for (int k = 0; k < kH; k += 4) {
@@ -183,6 +189,9 @@ __global__ void __launch_bounds__(kThreads, 1) rnnt_cluster_kernel(const RnntClP
           for (int rr = 0; rr < kCl; ++rr) cluster.map_shared_rank(&s.pg[u][rank * kHS + j], rr)[0] = v;
         }
         cluster.sync();
+#pragma unroll
+        for (int u = 0; u < kNU; ++u)
+          if (need_lstm[u] && t_u[u] < L[u]) hb[u] ^= 1;   // the fresh candidate is now the current one
       }
 
       // ---------------- joint: hid = relu(enc_proj[t] + pg), own class slice, local argmax
@@ -272,7 +281,7 @@ __global__ void __launch_bounds__(kThreads, 1) rnnt_cluster_kernel(const RnntClP
       // commit candidate state for utterances that emitted (their need_lstm was just set)
       for (int d = tid; d < kNU * kH; d += kThreads) {
         const int u = d / kH;
-        if (need_lstm[u]) s.h[u][d % kH] = s.hn[par][u][d % kH];
+        if (need_lstm[u]) s.h[u][d % kH] = s.hn[hb[u]][u][d % kH];
       }
       for (int d = tid; d < kNU * kHS; d += kThreads) {
         const int u = d / kHS;

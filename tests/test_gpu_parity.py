@@ -247,6 +247,27 @@ def test_rnnt_greedy_matches_reference_golden(eng_rnnt, golden_dir):
         assert frames[b, :n].tolist() == g[f"frames_{b}"].tolist()
 
 
+def test_rnnt_blank_then_emit_patterns(eng_rnnt, v2_rnnt_ckpt):
+    """Emissions that follow runs of blank frames consume a prediction-network state computed many steps earlier
+    (the synthetic audio never produces this: its encoder output is almost constant in time).  Random, time-varying
+    activations give hypotheses whose frame lists have gaps of both parities; ids and frames must still be exact."""
+    sd = v2_rnnt_ckpt["state_dict"]
+    gaps_seen = set()
+    for seed, scale in [(8, 0.5), (9, 0.5), (10, 0.4), (11, 0.6)]:
+        g = torch.Generator().manual_seed(seed)
+        enc = torch.randn(6, 40, 768, generator=g) * scale
+        enc_len = torch.tensor([40, 33, 0, 17, 40, 9], dtype=torch.int32)
+        want = orc.rnnt_greedy(enc.transpose(1, 2), enc_len, sd, 10)
+        ids, frames, counts = eng_rnnt.greedy(enc.cuda(), enc_len.cuda())
+        for b in range(6):
+            n = int(counts[b])
+            assert ids[b, :n].tolist() == want[b][0], (seed, b)
+            assert frames[b, :n].tolist() == want[b][1], (seed, b)
+            fr = want[b][1]
+            gaps_seen |= {(y - x) % 2 for x, y in zip(fr, fr[1:]) if y - x > 1}
+    assert gaps_seen == {0, 1}, "the test inputs no longer exercise blank runs of both parities"
+
+
 def test_rnnt_edge_lengths(eng_rnnt, v2_rnnt_ckpt):
     g = torch.Generator().manual_seed(8)
     enc = torch.randn(3, 20, 768, generator=g)
