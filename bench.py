@@ -166,6 +166,10 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # stdout must carry exactly ONE JSON line: libraries (NCCL prints its version banner on stdout) are diverted to stderr
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     n_samples = int(SECONDS * 16000)
     config = {"workload": f"{MODEL} batch={args.batch}x{SECONDS:g}s per GPU: log-mel + 16-layer Conformer encoder + CTC greedy "
                           "(BASELINE.json configs[1])",
@@ -183,7 +187,8 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "rtfx": res["rtfx"],
                 "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": res["value"], "unit": "utt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        real_stdout.write(json.dumps(line) + "\n")
+        real_stdout.flush()
         return 0
 
     import torch
@@ -360,7 +365,8 @@ def main():
                 "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
                 "roofline": roofline,
                 "cpu_baseline": ({k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")} if cpu else None)}
-        print(json.dumps(line))
+        real_stdout.write(json.dumps(line) + "\n")
+        real_stdout.flush()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -17,7 +17,7 @@ CSRC = PKG_DIR / "csrc"
 BUILD_DIR = PKG_DIR / "build"
 LIB_PATH = PKG_DIR / "libgigaam_b200.so"
 
-SOURCES = ["gam_api.cu", "gemm.cu", "attention_sm100.cu", "rowops.cu", "frontend.cu", "ctc.cu", "rnnt.cu", "rnnt_cluster.cu"]
+SOURCES = ["gam_api.cu", "gemm.cu", "attention_sm100.cu", "attention_relpos_sm100.cu", "rowops.cu", "frontend.cu", "ctc.cu", "rnnt.cu", "rnnt_cluster.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

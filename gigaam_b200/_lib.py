@@ -26,7 +26,10 @@ LAYER_FIELDS = (
     "ln_ff1_g", "ln_ff1_b", "ff1_w1", "ff1_b1", "ff1_w2", "ff1_b2",
     "ln_att_g", "ln_att_b", "w_qk", "b_qk", "w_v", "b_v", "w_o", "b_o",
     "ln_conv_g", "ln_conv_b", "pw1_w", "pw1_b", "dw_w", "dw_b", "cn_g", "cn_b", "pw2_w", "pw2_b",
-    "ln_ff2_g", "ln_ff2_b", "ff2_w1", "ff2_b1", "ff2_w2", "ff2_b2", "ln_out_g", "ln_out_b")
+    "ln_ff2_g", "ln_ff2_b", "ff2_w1", "ff2_b1", "ff2_w2", "ff2_b2", "ln_out_g", "ln_out_b",
+    "w_qkv_rel", "b_qkv_rel", "pos_proj")
+
+REL_POS_MAX_T = 640   # GAM_REL_POS_MAX_T in include/gigaam_b200.h
 
 
 class GamLayerWeights(C.Structure):
@@ -47,7 +50,7 @@ class GamWeights(C.Structure):
 EXPORTS = ("gam_create", "gam_destroy", "gam_last_error", "gam_version", "gam_logmel_frames", "gam_encoded_frames",
            "gam_workspace_bytes", "gam_logmel", "gam_encode", "gam_ctc_greedy", "gam_rnnt_greedy", "gam_test_gemm",
            "gam_test_attention", "gam_launch_count", "gam_profile_begin", "gam_profile_end", "gam_profile_class_count",
-           "gam_profile_class_name", "gam_logmel_workspace_bytes", "gam_logmel_tc")
+           "gam_profile_class_name", "gam_logmel_workspace_bytes", "gam_logmel_tc", "gam_test_attention_relpos")
 
 
 def lib_path() -> Path:
@@ -92,6 +95,8 @@ def load() -> C.CDLL:
     lib.gam_test_gemm.restype = C.c_int
     lib.gam_test_attention.argtypes = [H, c_vp, c_vp, c_vp, i32, i32, c_vp]
     lib.gam_test_attention.restype = C.c_int
+    lib.gam_test_attention_relpos.argtypes = [H, c_vp, c_vp, c_vp, c_vp, i32, i32, c_vp]
+    lib.gam_test_attention_relpos.restype = C.c_int
     lib.gam_logmel_workspace_bytes.argtypes = [H, i32, i64]
     lib.gam_logmel_workspace_bytes.restype = i64
     lib.gam_logmel_tc.argtypes = [H, c_vp, i32, i64, c_vp, c_vp, i64, c_vp]

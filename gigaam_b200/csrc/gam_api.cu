@@ -75,6 +75,7 @@ static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * 
 
 struct LayerMaps {
   CUtensorMap ff1_w1, ff1_w2, w_qk, w_v, w_o, pw1, pw2, ff2_w1, ff2_w2;
+  CUtensorMap w_qkv_rel, pos_proj;   // rel_pos attention only
 };
 
 struct Plan {
@@ -90,7 +91,7 @@ struct Plan {
   CUtensorMap m_melT, m_s1_3d;
   float* x = nullptr;
   int64_t bytes = 0;
-  CUtensorMap m_s1, m_s2, m_a16, m_r16, m_hid, m_qkv, m_o16;
+  CUtensorMap m_s1, m_s2, m_a16, m_r16, m_hid, m_qkv, m_qkv4, m_o16;
 };
 
 }  // namespace gam
@@ -179,7 +180,8 @@ void plan_geometry(const gam_handle* h, int B, int64_t M, Plan* p) {
 int64_t plan_carve(const gam_handle* h, Plan* p, uint8_t* base) {
   const gam_config& c = h->cfg;
   const int64_t d = c.d_model, R = p->R, B = p->B;
-  const int64_t wide = (c.d_ff > 3 * d ? c.d_ff : 3 * d);
+  const int64_t nqkv = (c.self_attention == 1 ? 4 : 3) * d;   // rel_pos carries q twice (q+u, q+v)
+  const int64_t wide = (c.d_ff > nqkv ? c.d_ff : nqkv);
   int64_t off = 0;
   auto take = [&](int64_t bytes) -> uint8_t* {
     uint8_t* ptr = base ? base + off : nullptr;
@@ -235,6 +237,7 @@ Plan* get_plan(gam_handle* h, int B, int64_t M, void* ws, int64_t ws_bytes) {
   rc |= make_tmap_2d_f16(&p->m_r16, p->r16, R, d, d, 128, 64);
   rc |= make_tmap_2d_f16(&p->m_hid, p->big16, R, c.d_ff, c.d_ff, 128, 64);
   rc |= make_tmap_2d_f16(&p->m_qkv, p->big16, R, 3 * d, 3 * d, 128, 64);
+  rc |= make_tmap_2d_f16(&p->m_qkv4, p->big16, R, 4 * d, 4 * d, 128, 64);
   rc |= make_tmap_2d_f16(&p->m_o16, p->o16, R, d, d, 128, 64);
   if (rc != 0) {
     fail(h, -2, "cuTensorMapEncodeTiled failed for activation maps (rc=%d)", rc);
@@ -277,7 +280,7 @@ int gam_create(const gam_config* cfg, const gam_weights* w, int device, gam_hand
   if (c.subsampling != 0 && c.subsampling != 1) return fail(h, -10, "unknown subsampling type %d", c.subsampling);
   if (c.subsampling == 1 && (c.feat_in % 64 != 0 || (c.subs_kernel_size & 1) == 0))
     return fail(h, -10, "conv1d subsampling needs feat_in %% 64 == 0 and an odd kernel size");
-  if (c.self_attention != 0) return fail(h, -10, "only rotary self-attention is built in this round");
+  if (c.self_attention != 0 && c.self_attention != 1) return fail(h, -10, "unknown self_attention type %d", c.self_attention);
   if (c.d_model != 768 || c.d_model % c.n_heads != 0 || (c.d_model / c.n_heads) % 16 != 0)
     return fail(h, -10, "unsupported d_model/n_heads (%d/%d): kernels are specialised for d_model 768, d_k %% 16 == 0",
                 c.d_model, c.n_heads);
@@ -300,8 +303,14 @@ int gam_create(const gam_config* cfg, const gam_weights* w, int device, gam_hand
     LayerMaps& lm = h->lmaps[l];
     rc |= make_tmap_2d_f16(&lm.ff1_w1, lw.ff1_w1, ff, d, d, 128, 64);
     rc |= make_tmap_2d_f16(&lm.ff1_w2, lw.ff1_w2, d, ff, ff, 128, 64);
-    rc |= make_tmap_2d_f16(&lm.w_qk, lw.w_qk, 2 * d, d, d, 128, 64);
-    rc |= make_tmap_2d_f16(&lm.w_v, lw.w_v, d, d, d, 128, 64);
+    if (c.self_attention == 0) {
+      rc |= make_tmap_2d_f16(&lm.w_qk, lw.w_qk, 2 * d, d, d, 128, 64);
+      rc |= make_tmap_2d_f16(&lm.w_v, lw.w_v, d, d, d, 128, 64);
+    } else {
+      if (!lw.w_qkv_rel || !lw.b_qkv_rel || !lw.pos_proj) return fail(h, -10, "layer %d: rel_pos weights missing", l);
+      rc |= make_tmap_2d_f16(&lm.w_qkv_rel, lw.w_qkv_rel, 4 * d, d, d, 128, 64);
+      rc |= make_tmap_2d_f16(&lm.pos_proj, lw.pos_proj, 2 * kRelPosMaxT - 1, d, d, 128, 64);
+    }
     rc |= make_tmap_2d_f16(&lm.w_o, lw.w_o, d, d, d, 128, 64);
     rc |= make_tmap_2d_f16(&lm.pw1, lw.pw1_w, 2 * d, d, d, 128, 64);
     rc |= make_tmap_2d_f16(&lm.pw2, lw.pw2_w, d, d, d, 128, 64);
@@ -479,14 +488,24 @@ int gam_encode(gam_handle* h, const float* mel, const int64_t* mel_len, int32_t 
     { PROF(PC_GEMM_FFN_DOWN);
       rc |= launch_gemm(GEMM_BIAS_RES_F32, &p->m_hid, &m.ff1_w2, R, d, c.d_ff, w.ff1_b2, p->x, p->x, d, 0.5f, nsm, s); }
     // x += W_o attn(q = W_q rope(u), k = W_k rope(u), v = W_v u), u = LN(x)   (encoder.py:485-487, 236-277)
-    { PROF(PC_LAYERNORM);
-      launch_ln_rope_f16(p->x, w.ln_att_g, w.ln_att_b, h->w.rope_cos, h->w.rope_sin, p->a16, p->r16, R, p->T2, dk / 2, s); }
-    { PROF(PC_GEMM_QKV);
-      rc |= launch_gemm(GEMM_BIAS_F16, &p->m_r16, &m.w_qk, R, 2 * d, d, w.b_qk, nullptr, p->big16, 3 * d, 1.f, nsm, s); }
-    { PROF(PC_GEMM_QKV);
-      rc |= launch_gemm(GEMM_BIAS_F16, &p->m_a16, &m.w_v, R, d, d, w.b_v, nullptr, p->big16 + 2 * d, 3 * d, 1.f, nsm, s); }
-    { PROF(PC_ATTENTION);
-      rc |= launch_attention(&p->m_qkv, B > 1 ? p->len2 : nullptr, p->o16, B, p->T2, c.n_heads, dk, d, s); }
+    if (c.self_attention == 0) {
+      { PROF(PC_LAYERNORM);
+        launch_ln_rope_f16(p->x, w.ln_att_g, w.ln_att_b, h->w.rope_cos, h->w.rope_sin, p->a16, p->r16, R, p->T2, dk / 2, s); }
+      { PROF(PC_GEMM_QKV);
+        rc |= launch_gemm(GEMM_BIAS_F16, &p->m_r16, &m.w_qk, R, 2 * d, d, w.b_qk, nullptr, p->big16, 3 * d, 1.f, nsm, s); }
+      { PROF(PC_GEMM_QKV);
+        rc |= launch_gemm(GEMM_BIAS_F16, &p->m_a16, &m.w_v, R, d, d, w.b_v, nullptr, p->big16 + 2 * d, 3 * d, 1.f, nsm, s); }
+      { PROF(PC_ATTENTION);
+        rc |= launch_attention(&p->m_qkv, B > 1 ? p->len2 : nullptr, p->o16, B, p->T2, c.n_heads, dk, d, s); }
+    } else {
+      // rel_pos (encoder.py:208-228): one projection GEMM -> [q+u | q+v | k | v], position scores inside the kernel
+      { PROF(PC_LAYERNORM);
+        launch_ln_f16(p->x, w.ln_att_g, w.ln_att_b, p->a16, R, s); }
+      { PROF(PC_GEMM_QKV);
+        rc |= launch_gemm(GEMM_BIAS_F16, &p->m_a16, &m.w_qkv_rel, R, 4 * d, d, w.b_qkv_rel, nullptr, p->big16, 4 * d, 1.f, nsm, s); }
+      { PROF(PC_ATTENTION);
+        rc |= launch_attention_relpos(&p->m_qkv4, &m.pos_proj, B > 1 ? p->len2 : nullptr, p->o16, B, p->T2, c.n_heads, dk, d, s); }
+    }
     { PROF(PC_GEMM_PROJ);
       rc |= launch_gemm(GEMM_BIAS_RES_F32, &p->m_o16, &m.w_o, R, d, d, w.b_o, p->x, p->x, d, 1.f, nsm, s); }
     // x += Conv(LN(x))                                           (encoder.py:489-491, 396-409)
@@ -639,6 +658,24 @@ int gam_test_attention(gam_handle* h, const void* qkv, const int32_t* klen, void
   }
   if (rc) return fail(h, -4, "attention launch rejected (T=%d)", T);
   GAM_CHECK_LAUNCH(h, "test_attention");
+  return 0;
+}
+
+int gam_test_attention_relpos(gam_handle* h, const void* qkv, const void* pos, const int32_t* klen, void* out, int32_t B,
+                              int32_t T, void* stream) {
+  const gam_config& c = h->cfg;
+  CUtensorMap tq, tp;
+  const uint64_t d = c.d_model;
+  int rc = make_tmap_2d_f16(&tq, qkv, static_cast<uint64_t>(B) * T, 4 * d, 4 * d, 128, 64);
+  rc |= make_tmap_2d_f16(&tp, pos, 2 * kRelPosMaxT - 1, d, d, 128, 64);
+  if (rc) return fail(h, -2, "tensor map encode failed (rc=%d)", rc);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  {
+    PROF(PC_ATTENTION);
+    rc = launch_attention_relpos(&tq, &tp, klen, static_cast<__half*>(out), B, T, c.n_heads, c.d_model / c.n_heads, c.d_model, s);
+  }
+  if (rc) return fail(h, -4, "rel_pos attention launch rejected (T=%d, rc=%d)", T, rc);
+  GAM_CHECK_LAUNCH(h, "test_attention_relpos");
   return 0;
 }
 

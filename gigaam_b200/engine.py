@@ -71,6 +71,26 @@ def split_dft_basis(n_fft: int) -> Tensor:
     return torch.cat([hi, hi, lo], dim=1).contiguous()
 
 
+def rel_pos_embedding(max_t: int, d: int) -> Tensor:
+    """Sinusoids of the relative positions max_t-1 ... -(max_t-1), row max_t-1-r for position r, sin on even / cos on
+    odd columns (gigaam/encoder.py:318-326).  The reference slices the same rows out of its pos_emb_max_len table
+    (:329-334), so the projected table below serves every T' <= max_t."""
+    pos = torch.arange(max_t - 1, -max_t, -1, dtype=torch.float32).unsqueeze(1)
+    div = torch.exp(torch.arange(0, d, 2, dtype=torch.float32) * -(math.log(10000.0) / d))
+    pe = torch.zeros(2 * max_t - 1, d)
+    pe[:, 0::2] = torch.sin(pos * div)
+    pe[:, 1::2] = torch.cos(pos * div)
+    return pe
+
+
+def pack_rel_pos_qkv(wq: Tensor, bq: Tensor, wk: Tensor, bk: Tensor, wv: Tensor, bv: Tensor, bias_u: Tensor, bias_v: Tensor):
+    """One projection for the rel_pos attention: rows [q ; q ; k ; v] with pos_bias_u / pos_bias_v (gigaam/encoder.py:
+    221-222, [h, d_k] = the d_model axis split by head) folded into the two q biases -> ([4d, d], [4d])."""
+    w = torch.cat([wq, wq, wk, wv], 0)
+    b = torch.cat([bq + bias_u.reshape(-1), bq + bias_v.reshape(-1), bk, bv], 0)
+    return w, b
+
+
 def rotary_half_tables(dk: int, base: float, max_len: int):
     """cos/sin [max_len, dk/2] of t * base^(-2i/dk) (gigaam/encoder.py:342-355; base = pos_emb_max_len)."""
     inv_freq = 1.0 / (base ** (torch.arange(0, dk, 2).float() / dk))
@@ -102,8 +122,10 @@ class Engine:
         self.n_layers = enc["n_layers"]
         self.n_heads = enc["n_heads"]
         self.d_ff = self.d_model * enc["ff_expansion_factor"]
-        if enc["self_attention_model"] != "rotary":
-            raise NotImplementedError("rel_pos self-attention (v1_* checkpoints) is not built yet")
+        if enc["self_attention_model"] not in ("rotary", "rel_pos"):
+            raise ValueError(f"unknown self_attention_model {enc['self_attention_model']!r}")
+        self.rel_pos = enc["self_attention_model"] == "rel_pos"
+        self._pos_emb = rel_pos_embedding(_lib.REL_POS_MAX_T, self.d_model).to(device) if self.rel_pos else None
         self.head_type = 0
         self.num_classes = 0
         self.max_symbols = 10
@@ -114,7 +136,7 @@ class Engine:
         gc.subs_kernel_size = enc["subs_kernel_size"]
         gc.conv_kernel_size = enc["conv_kernel_size"]
         gc.conv_norm = 0 if enc["conv_norm_type"] == "batch_norm" else 1
-        gc.self_attention = 0
+        gc.self_attention = 1 if self.rel_pos else 0
         gc.pos_emb_max_len = enc["pos_emb_max_len"]
         gw = _lib.GamWeights()
         sd = state_dict
@@ -212,9 +234,20 @@ class Engine:
         lw.ff1_w1, lw.ff1_b1 = self._dev(f("feed_forward1.linear1.weight"), h16), self._dev(f("feed_forward1.linear1.bias"))
         lw.ff1_w2, lw.ff1_b2 = self._dev(f("feed_forward1.linear2.weight"), h16), self._dev(f("feed_forward1.linear2.bias"))
         lw.ln_att_g, lw.ln_att_b = self._dev(f("norm_self_att.weight")), self._dev(f("norm_self_att.bias"))
-        lw.w_qk = self._dev(torch.cat([f("self_attn.linear_q.weight"), f("self_attn.linear_k.weight")], 0), h16)
-        lw.b_qk = self._dev(torch.cat([f("self_attn.linear_q.bias"), f("self_attn.linear_k.bias")], 0))
-        lw.w_v, lw.b_v = self._dev(f("self_attn.linear_v.weight"), h16), self._dev(f("self_attn.linear_v.bias"))
+        if self.rel_pos:
+            w4, b4 = pack_rel_pos_qkv(f("self_attn.linear_q.weight"), f("self_attn.linear_q.bias"),
+                                      f("self_attn.linear_k.weight"), f("self_attn.linear_k.bias"),
+                                      f("self_attn.linear_v.weight"), f("self_attn.linear_v.bias"),
+                                      f("self_attn.pos_bias_u"), f("self_attn.pos_bias_v"))
+            lw.w_qkv_rel, lw.b_qkv_rel = self._dev(w4, h16), self._dev(b4)
+            # linear_pos (no bias, encoder.py:198,219) of a constant table is a constant: projected once at load time
+            lw.pos_proj = self._dev(self._pos_emb @ f("self_attn.linear_pos.weight").to(self.device).t(), h16)
+            lw.w_qk = lw.b_qk = lw.w_v = lw.b_v = None
+        else:
+            lw.w_qk = self._dev(torch.cat([f("self_attn.linear_q.weight"), f("self_attn.linear_k.weight")], 0), h16)
+            lw.b_qk = self._dev(torch.cat([f("self_attn.linear_q.bias"), f("self_attn.linear_k.bias")], 0))
+            lw.w_v, lw.b_v = self._dev(f("self_attn.linear_v.weight"), h16), self._dev(f("self_attn.linear_v.bias"))
+            lw.w_qkv_rel = lw.b_qkv_rel = lw.pos_proj = None
         lw.w_o, lw.b_o = self._dev(f("self_attn.linear_out.weight"), h16), self._dev(f("self_attn.linear_out.bias"))
         lw.ln_conv_g, lw.ln_conv_b = self._dev(f("norm_conv.weight")), self._dev(f("norm_conv.bias"))
         # GLU pairing: accumulator tile j (256 columns) = [value rows j*128.. | gate rows d + j*128..]

@@ -31,9 +31,10 @@ def _encoder_cfg(version: str) -> Dict:
         return dict(feat_in=64, n_layers=16, d_model=768, subsampling="conv1d", subs_kernel_size=5,
                     subsampling_factor=4, ff_expansion_factor=4, self_attention_model="rotary", n_heads=16,
                     pos_emb_max_len=5000, conv_norm_type="layer_norm", conv_kernel_size=5, flash_attn=False)
+    # v1: the Transformer-XL relative-position attention of gigaam/encoder.py:191-228 (RECALLED to be the v1_* setting)
     return dict(feat_in=64, n_layers=16, d_model=768, subsampling="conv2d", subs_kernel_size=3,
-                subsampling_factor=4, ff_expansion_factor=4, self_attention_model="rotary", n_heads=16,
-                pos_emb_max_len=5000, conv_norm_type="batch_norm", conv_kernel_size=31, flash_attn=False)
+                subsampling_factor=4, ff_expansion_factor=4, self_attention_model="rel_pos" if version == "v1" else "rotary",
+                n_heads=16, pos_emb_max_len=5000, conv_norm_type="batch_norm", conv_kernel_size=31, flash_attn=False)
 
 
 def model_cfg(model_name: str, n_layers: int | None = None) -> Dict:
@@ -41,7 +42,7 @@ def model_cfg(model_name: str, n_layers: int | None = None) -> Dict:
     version = model_name.split("_")[0]
     if version not in ("v1", "v2", "v3"):
         raise ValueError(f"unknown synthetic model {model_name!r}")
-    enc = _encoder_cfg("v3" if version == "v3" else "v2")
+    enc = _encoder_cfg(version)
     if n_layers is not None:
         enc["n_layers"] = n_layers
     pre = dict(sample_rate=SAMPLE_RATE, features=64)
@@ -153,6 +154,13 @@ def encoder_param_list(enc: Dict) -> List[Tuple[str, Tuple[int, ...], str, float
         ln(q + "norm_self_att")
         for nm in ("linear_q", "linear_k", "linear_v", "linear_out"):
             lin(q + "self_attn." + nm, d, d)
+        if enc["self_attention_model"] == "rel_pos":
+            # the reference leaves pos_bias_u / pos_bias_v uninitialised (torch.FloatTensor, encoder.py:199-200); a
+            # checkpoint always overwrites them, so the synthetic one draws them like biases
+            dk = d // enc["n_heads"]
+            lin(q + "self_attn.linear_pos", d, d, bias=False)
+            out.append((q + "self_attn.pos_bias_u", (enc["n_heads"], dk), "b", dk))
+            out.append((q + "self_attn.pos_bias_v", (enc["n_heads"], dk), "b", dk))
         ln(q + "norm_feed_forward2")
         lin(q + "feed_forward2.linear1", ff, d)
         lin(q + "feed_forward2.linear2", d, ff)

@@ -37,7 +37,7 @@ typedef struct gam_config {
   int32_t subs_kernel_size; /* 3 (conv2d) */
   int32_t conv_kernel_size; /* depthwise taps: 31 or 5 */
   int32_t conv_norm;        /* 0 = batch_norm (folded into the depthwise conv), 1 = layer_norm */
-  int32_t self_attention;   /* 0 = rotary */
+  int32_t self_attention;   /* 0 = rotary, 1 = rel_pos (v1 checkpoints) */
   int32_t pos_emb_max_len;
   /* head (gigaam/decoder.py) */
   int32_t head;        /* 0 = none (ssl), 1 = ctc, 2 = rnnt */
@@ -73,7 +73,14 @@ typedef struct gam_layer_weights {
   const void* ff2_w2;
   const float* ff2_b2;
   const float *ln_out_g, *ln_out_b;
+  /* self_attention == 1 (rel_pos, gigaam/encoder.py:191-228) only, else NULL; w_qk / w_v are then unused */
+  const void* w_qkv_rel;  /* h [4d, d] = [linear_q ; linear_q ; linear_k ; linear_v] */
+  const float* b_qkv_rel; /* f [4d]    = [b_q + pos_bias_u ; b_q + pos_bias_v ; b_k ; b_v] */
+  const void* pos_proj;   /* h [2*GAM_REL_POS_MAX_T-1, d]: linear_pos(pe(r)), row GAM_REL_POS_MAX_T-1-r for relative
+                           * position r (pe = gigaam/encoder.py:318-326) */
 } gam_layer_weights;
+
+#define GAM_REL_POS_MAX_T 640 /* longest T' the rel_pos attention kernel serves (5 key blocks of 128) */
 
 typedef struct gam_weights {
   /* front end */
@@ -161,6 +168,9 @@ int gam_test_gemm(gam_handle* h, int32_t kind, const void* A, const void* W, con
                   int32_t M, int32_t N, int32_t K, int32_t ldo, float scale, void* stream);
 /* qkv: f16 [B*T, 3*d_model]; klen i32 [B] or NULL -> out f16 [B*T, d_model] */
 int gam_test_attention(gam_handle* h, const void* qkv, const int32_t* klen, void* out, int32_t B, int32_t T, void* stream);
+/* rel_pos variant: qkv f16 [B*T, 4*d_model] = [q+u | q+v | k | v]; pos f16 [2*GAM_REL_POS_MAX_T-1, d_model] */
+int gam_test_attention_relpos(gam_handle* h, const void* qkv, const void* pos, const int32_t* klen, void* out, int32_t B,
+                              int32_t T, void* stream);
 /* number of kernels this handle has launched so far (bench.py's gpu_launches) */
 int64_t gam_launch_count(const gam_handle* h);
 

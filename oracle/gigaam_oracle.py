@@ -138,6 +138,43 @@ def rotary_mhsa(u: Tensor, sd: SD, q: str, n_heads: int, cos: Tensor, sin: Tenso
     return F.linear(o, sd[q + "linear_out.weight"], sd[q + "linear_out.bias"])
 
 
+def rel_pos_table(t: int, d: int) -> Tensor:
+    """gigaam/encoder.py:312-334: sinusoids of the relative positions t-1 ... -(t-1) (the slice forward() cuts out of
+    the pos_emb_max_len table), sin on even / cos on odd columns, frequencies 10000^(-2i/d).  [2t-1, d]"""
+    pos = torch.arange(t - 1, -t, -1, dtype=torch.float32).unsqueeze(1)
+    div = torch.exp(torch.arange(0, d, 2, dtype=torch.float32) * -(math.log(10000.0) / d))
+    pe = torch.zeros(2 * t - 1, d)
+    pe[:, 0::2] = torch.sin(pos * div)
+    pe[:, 1::2] = torch.cos(pos * div)
+    return pe
+
+
+def rel_pos_mhsa(u: Tensor, sd: SD, q: str, n_heads: int, pos_emb: Tensor, key_valid: Optional[Tensor]) -> Tensor:
+    """gigaam/encoder.py:208-228 (+ :159-188): Transformer-XL scores
+        s[i, j] = ((q_i + u) . k_j + (q_i + v) . p_{i-j}) / sqrt(d_k),   p_r = W_pos pe(r),
+    written with the explicit index the reference's pad/view `rel_shift` (:202-206) produces: row i of the
+    [T, 2T-1] position scores is read at column T-1-i+j.  Padded keys are excluded (the reference fills them with
+    -10000 before the softmax and zeroes them after it, :182-183, which is the same on every valid query row)."""
+    b, t, d = u.shape
+    dk = d // n_heads
+    qh = F.linear(u, sd[q + "linear_q.weight"], sd[q + "linear_q.bias"]).view(b, t, n_heads, dk)
+    kh = F.linear(u, sd[q + "linear_k.weight"], sd[q + "linear_k.bias"]).view(b, t, n_heads, dk).transpose(1, 2)
+    vh = F.linear(u, sd[q + "linear_v.weight"], sd[q + "linear_v.bias"]).view(b, t, n_heads, dk).transpose(1, 2)
+    p = F.linear(pos_emb, sd[q + "linear_pos.weight"]).view(2 * t - 1, n_heads, dk).transpose(0, 1)   # [h, 2t-1, dk]
+    qu = (qh + sd[q + "pos_bias_u"]).transpose(1, 2)                                                   # [b, h, t, dk]
+    qv = (qh + sd[q + "pos_bias_v"]).transpose(1, 2)
+    ac = torch.matmul(qu, kh.transpose(-2, -1))
+    bd_raw = torch.matmul(qv, p.transpose(-2, -1))                                                      # [b, h, t, 2t-1]
+    idx = (t - 1) - torch.arange(t)[:, None] + torch.arange(t)[None, :]                                 # [t, t]
+    bd = torch.gather(bd_raw, 3, idx.expand(b, n_heads, t, t))
+    scores = (ac + bd) / math.sqrt(dk)
+    if key_valid is not None:
+        scores = scores.masked_fill(~key_valid[:, None, None, :], float("-inf"))
+    o = torch.matmul(torch.softmax(scores, dim=-1), vh)
+    o = o.transpose(1, 2).reshape(b, t, d)
+    return F.linear(o, sd[q + "linear_out.weight"], sd[q + "linear_out.bias"])
+
+
 def conv_module(u: Tensor, sd: SD, q: str, enc: Dict, pad_mask: Tensor) -> Tensor:
     """gigaam/encoder.py:396-409"""
     x = u.transpose(1, 2)
@@ -171,7 +208,10 @@ def conformer_layer(x: Tensor, sd: SD, l: int, enc: Dict, cos: Tensor, sin: Tens
     """gigaam/encoder.py:473-498"""
     q = f"encoder.layers.{l}."
     r = x + 0.5 * _ff(_ln(x, sd, q + "norm_feed_forward1"), sd, q + "feed_forward1")
-    r = r + rotary_mhsa(_ln(r, sd, q + "norm_self_att"), sd, q + "self_attn.", enc["n_heads"], cos, sin, key_valid)
+    if enc["self_attention_model"] == "rotary":
+        r = r + rotary_mhsa(_ln(r, sd, q + "norm_self_att"), sd, q + "self_attn.", enc["n_heads"], cos, sin, key_valid)
+    else:   # rel_pos: `cos` carries the [2T-1, d] position table
+        r = r + rel_pos_mhsa(_ln(r, sd, q + "norm_self_att"), sd, q + "self_attn.", enc["n_heads"], cos, key_valid)
     r = r + conv_module(_ln(r, sd, q + "norm_conv"), sd, q + "conv.", enc, pad_mask)
     r = r + 0.5 * _ff(_ln(r, sd, q + "norm_feed_forward2"), sd, q + "feed_forward2")
     return _ln(r, sd, q + "norm_out")
@@ -180,12 +220,13 @@ def conformer_layer(x: Tensor, sd: SD, l: int, enc: Dict, cos: Tensor, sin: Tens
 def encoder_forward(mel: Tensor, mel_len: Tensor, sd: SD, enc: Dict, n_layers_run: Optional[int] = None,
                     return_all: bool = False):
     """gigaam/encoder.py:605-647.  Returns ([B, d, T'], len int32) (+ list of [B, T', d] per stage)."""
-    if enc["self_attention_model"] != "rotary":
-        raise NotImplementedError("rel_pos attention (v1_*) is outside this round's scope")
     x, length = pre_encode(mel, mel_len, sd, enc)
     stages = [x]
     t = x.size(1)
-    cos, sin = rotary_tables(enc["pos_emb_max_len"], enc["d_model"] // enc["n_heads"], enc["pos_emb_max_len"])
+    if enc["self_attention_model"] == "rotary":
+        cos, sin = rotary_tables(enc["pos_emb_max_len"], enc["d_model"] // enc["n_heads"], enc["pos_emb_max_len"])
+    else:
+        cos, sin = rel_pos_table(t, enc["d_model"]), None
     valid = torch.arange(t)[None, :] < length[:, None]
     key_valid = valid if x.shape[0] > 1 else None
     pad_mask = ~valid

@@ -125,7 +125,13 @@ def run_case(model_name: str, batch: int, seconds: float, ragged: bool, out_name
 
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count() or 8)
-    run_case("v2_ctc", batch=2, seconds=2.0, ragged=True, out_name="v2_ctc_b2_2s.npz")
-    run_case("v2_rnnt", batch=2, seconds=2.0, ragged=True, out_name="v2_rnnt_b2_2s.npz")
-    # v3 shape (RECALLED): conv1d k5 subsampling, LayerNorm conv-norm, depthwise k5, n_fft 320, center=False
-    run_case("v3_e2e_rnnt", batch=2, seconds=2.0, ragged=True, out_name="v3_e2e_rnnt_b2_2s.npz")
+    cases = {
+        "v2_ctc": dict(batch=2, seconds=2.0, ragged=True, out_name="v2_ctc_b2_2s.npz"),
+        "v2_rnnt": dict(batch=2, seconds=2.0, ragged=True, out_name="v2_rnnt_b2_2s.npz"),
+        # v3 shape (RECALLED): conv1d k5 subsampling, LayerNorm conv-norm, depthwise k5, n_fft 320, center=False
+        "v3_e2e_rnnt": dict(batch=2, seconds=2.0, ragged=True, out_name="v3_e2e_rnnt_b2_2s.npz"),
+        # v1 shape: the rel_pos attention branch (encoder.py:191-228, 307-334); 6 s so that T' = 151 spans two key blocks
+        "v1_ctc": dict(batch=2, seconds=6.0, ragged=True, out_name="v1_ctc_b2_6s.npz"),
+    }
+    for name in (sys.argv[1:] or list(cases)):
+        run_case(name, **cases[name])

@@ -26,5 +26,11 @@ def v2_rnnt_ckpt():
 
 
 @pytest.fixture(scope="session")
+def v1_ctc_ckpt():
+    from gigaam_b200 import synthetic
+    return synthetic.synthetic_checkpoint("v1_ctc", seed=0)
+
+
+@pytest.fixture(scope="session")
 def golden_dir():
     return ROOT / "tests" / "golden"

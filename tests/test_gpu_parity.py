@@ -395,3 +395,91 @@ def test_v3_rnnt_greedy_matches_reference_golden(eng_v3, golden_dir):
         assert ids[b, :n].tolist() == g[f"ids_{b}"].tolist()
         assert frames[b, :n].tolist() == g[f"frames_{b}"].tolist()
     assert total > 0
+
+
+# ------------------------------------------------------------------------------------------ v1 shape: rel_pos attention
+@pytest.fixture(scope="session")
+def eng_v1(dev, v1_ctc_ckpt):
+    return Engine(v1_ctc_ckpt["cfg"], v1_ctc_ckpt["state_dict"], dev)
+
+
+@pytest.mark.parametrize("B,T,lens", [(1, 128, None), (2, 51, [51, 30]), (3, 251, [251, 200, 97]), (2, 376, [376, 129]),
+                                      (1, 626, None), (2, 5, [5, 1]), (2, 129, [129, 128]), (3, 300, [300, 0, 257]), (1, 640, None)])
+def test_relpos_attention_matches_shifted_softmax(eng_v1, dev, B, T, lens):
+    """gam_test_attention_relpos vs the reference formula (gigaam/encoder.py:216-228) in torch fp32, with the
+    reference's own pad/view rel_shift, on the same fp16 operands."""
+    from gigaam_b200 import _lib
+    g = torch.Generator().manual_seed(B * 1000 + T + 7)
+    d, H, dk, L = 768, 16, 48, _lib.REL_POS_MAX_T
+    qkv = torch.randn(B * T, 4 * d, generator=g).half().to(dev)
+    pos = torch.randn(2 * L - 1, d, generator=g).half().to(dev)
+    out = torch.zeros(B * T, d, dtype=torch.float16, device=dev)
+    klen = torch.tensor(lens, dtype=torch.int32, device=dev) if lens else None
+    rc = eng_v1.lib.gam_test_attention_relpos(eng_v1.handle, qkv.data_ptr(), pos.data_ptr(), klen.data_ptr() if lens else None,
+                                              out.data_ptr(), B, T, _stream())
+    torch.cuda.synchronize()
+    assert rc == 0
+    x = qkv.float().view(B, T, 4, H, dk)
+    qu, qv, k, v = (x[:, :, i].transpose(1, 2) for i in range(4))
+    p = pos.float()[L - T: L + T - 1].view(2 * T - 1, H, dk).transpose(0, 1)            # positions T-1 ... -(T-1)
+    bd = qv @ p.transpose(-1, -2)                                                        # [B, H, T, 2T-1]
+    bd = F.pad(bd, (1, 0)).view(B, H, -1, T)[:, :, 1:].reshape(B, H, T, 2 * T - 1)[..., :T]   # rel_shift, encoder.py:202-206
+    sc = (qu @ k.transpose(-1, -2) + bd) / dk ** 0.5
+    valid = torch.ones(B, T, dtype=torch.bool, device=dev)
+    if lens:
+        valid = torch.arange(T, device=dev)[None, :] < klen[:, None]
+        sc = sc.masked_fill(~valid[:, None, None, :], float("-inf"))
+    want = (torch.softmax(sc, -1).nan_to_num(0.0) @ v).transpose(1, 2).reshape(B, T, d)
+    got = out.float().view(B, T, d)
+    assert torch.isfinite(out).all()
+    has_keys = (valid.sum(1) > 0)
+    assert rel(got[has_keys], want[has_keys]) < 1e-3
+    assert float(got[~has_keys].abs().max()) == 0.0 if (~has_keys).any() else True   # no valid key -> zeros
+
+
+def test_v1_rel_pos_encoder_against_reference_golden(eng_v1, v1_ctc_ckpt, golden_dir):
+    """wav -> ids of the rel_pos model vs outputs of the REAL reference (tests/golden/v1_ctc_b2_6s.npz)."""
+    g = np.load(golden_dir / "v1_ctc_b2_6s.npz")
+    cfg, sd = v1_ctc_ckpt["cfg"], v1_ctc_ckpt["state_dict"]
+    wav, wav_len = synthetic.synthetic_audio(2, 6.0, seed=1234, ragged=True)
+    mel = eng_v1.logmel(wav.cuda())
+    assert float((mel.cpu() - torch.from_numpy(g["mel"])).abs().max()) < 5e-3
+    mel_ref, mel_len = torch.from_numpy(g["mel"]), torch.from_numpy(g["mel_len"])
+    with torch.inference_mode():
+        _, len_o, stages = orc.encoder_forward(mel_ref, mel_len, sd, cfg["encoder"], n_layers_run=2, return_all=True)
+    valid = torch.arange(stages[0].shape[1])[None, :] < len_o[:, None]
+    for n in (1, 2):
+        e, _ = eng_v1.encode(mel_ref.cuda(), mel_len.cuda(), n_layers_run=n)
+        assert rel(e.cpu()[valid], stages[n][valid]) < ENC_REL_TOL, f"after {n} layers"
+    enc, enc_len = eng_v1.encode(mel, mel_len.cuda())
+    assert np.array_equal(enc_len.cpu().numpy(), g["enc_len"])
+    want = torch.from_numpy(g["enc"]).transpose(1, 2)
+    assert torch.isfinite(enc).all()
+    assert rel(enc.cpu()[valid], want[valid]) < ENC_REL_TOL
+    ids, frames, counts = eng_v1.greedy(enc, enc_len)
+    margin = torch.from_numpy(g["ctc_margin"])
+    for b in range(2):
+        n = int(counts[b])
+        if float(margin[b][: int(g["enc_len"][b])].min()) > 2e-3:
+            assert ids[b, :n].tolist() == g[f"ids_{b}"].tolist()
+            assert frames[b, :n].tolist() == g[f"frames_{b}"].tolist()
+
+
+def test_v1_batch_vs_single_and_long(eng_v1):
+    """rel_pos path: a ragged batch agrees with its utterances run alone (atol 0.03 is the reference's own bar,
+    tests/test_batching.py:70), and a 25 s utterance (T' = 626, five key blocks) stays finite."""
+    wav, wav_len = synthetic.synthetic_audio(3, 4.0, seed=5, ragged=True)
+    mel = eng_v1.logmel(wav.cuda())
+    mel_len = torch.tensor([eng_v1.logmel_frames(int(n)) for n in wav_len])
+    enc, enc_len = eng_v1.encode(mel, mel_len.cuda())
+    for b in range(3):
+        m = int(mel_len[b])
+        e1, l1 = eng_v1.encode(mel[b:b + 1, :, :m].contiguous(), torch.tensor([m]).cuda())   # same front-end frames, alone
+        n = int(l1[0])
+        assert n == int(enc_len[b])
+        assert float((e1[0, :n] - enc[b, :n]).abs().max()) < 0.03
+        assert rel(e1[0, :n], enc[b, :n]) < 2e-3
+    wav, _ = synthetic.synthetic_audio(1, 25.0, seed=6)
+    mel = eng_v1.logmel(wav.cuda())
+    enc, enc_len = eng_v1.encode(mel, torch.tensor([mel.shape[2]]).cuda())
+    assert int(enc_len[0]) == 626 and torch.isfinite(enc).all()

@@ -64,6 +64,32 @@ def test_rnnt_greedy_matches_reference(golden_dir, v2_rnnt_ckpt):
     assert total > 0  # the calibrated blank bias must leave a non-degenerate hypothesis
 
 
+def test_rel_pos_encoder_matches_reference(golden_dir, v1_ctc_ckpt):
+    """v1 shape: the oracle's explicit-index rel_shift against the reference's pad/view one (encoder.py:202-228),
+    full 16-layer stack on the reference's own log-mel against its encoder output."""
+    g = np.load(golden_dir / "v1_ctc_b2_6s.npz")
+    cfg, sd = v1_ctc_ckpt["cfg"], v1_ctc_ckpt["state_dict"]
+    assert cfg["encoder"]["self_attention_model"] == "rel_pos"
+    with torch.inference_mode():
+        enc, enc_len = orc.encoder_forward(torch.from_numpy(g["mel"]), torch.from_numpy(g["mel_len"]), sd, cfg["encoder"])
+    assert np.array_equal(enc_len.numpy(), g["enc_len"])
+    valid = torch.arange(enc.shape[2])[None, :] < enc_len[:, None]
+    assert _rel(enc.transpose(1, 2)[valid], torch.from_numpy(g["enc"]).transpose(1, 2)[valid]) < 1e-5
+    hyp = orc.ctc_greedy(torch.from_numpy(g["enc"]), torch.from_numpy(g["enc_len"]), sd)
+    for b, (ids, frames) in enumerate(hyp):
+        assert ids == g[f"ids_{b}"].tolist() and frames == g[f"frames_{b}"].tolist()
+
+
+def test_rel_shift_index_matches_pad_view_trick():
+    """The reference's rel_shift (pad one column, view as [2T, T], drop the first row) equals reading column
+    T-1-i+j of row i -- the index the CUDA kernel skews its position scores by."""
+    t = 7
+    x = torch.arange(2 * 3 * t * (2 * t - 1), dtype=torch.float32).view(2, 3, t, 2 * t - 1)
+    y = torch.nn.functional.pad(x, pad=(1, 0)).view(2, 3, -1, t)[:, :, 1:].view(2, 3, t, 2 * t - 1)[..., :t]
+    idx = (t - 1) - torch.arange(t)[:, None] + torch.arange(t)[None, :]
+    assert torch.equal(y, torch.gather(x, 3, idx.expand(2, 3, t, t)))
+
+
 def test_ctc_collapse_edge_cases(v2_ctc_ckpt):
     """Empty lengths, length 1, repeated labels, all blanks (gigaam/decoding.py:76-91 semantics)."""
     sd = v2_ctc_ckpt["state_dict"]
