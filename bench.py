@@ -360,7 +360,7 @@ def main():
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "utt/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "api": "gigaam_b200.pipeline.BatchPipeline over model(wav, len) + model.decoding: pinned host wav in, python "
-                               "hypotheses out, copies of neighbouring steps overlapped with compute",
+                               "hypotheses out, copies of neighbouring steps overlapped with compute, kernels replayed as one CUDA graph per shape",
                         "serial_value": e2e_serial_value},
                 "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
                 "roofline": roofline,

@@ -9,6 +9,7 @@
 
 #include "../../include/gigaam_b200.h"
 #include "kernels.h"
+#include "launch.cuh"
 
 namespace gam {
 
@@ -109,6 +110,8 @@ struct gam_handle {
   int64_t lm_F = 0;
   int device = 0;
   int num_sms = 148;
+  size_t l2_persist_bytes = 0;   // persisting-L2 carve-out granted at create (0 = feature off)
+  size_t l2_window_max = 0;
   int64_t launches = 0;
   std::string err;
   std::vector<Plan*> plans;
@@ -291,6 +294,23 @@ int gam_create(const gam_config* cfg, const gam_weights* w, int device, gam_hand
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(h, -11, "cudaGetDeviceProperties failed");
   if (prop.major != 10) return fail(h, -12, "sm_100a kernels need a Blackwell (cc 10.x) device, found cc %d.%d", prop.major, prop.minor);
   h->num_sms = prop.multiProcessorCount;
+  {
+    // L2 residency of the residual stream (launch.cuh).  Opt-in (GAM_L2_PERSIST=1, carve-out GAM_L2_PERSIST_MB): measured on
+    // c2 the residual GEMMs gain (proj 1.28 -> 1.05 ms) but the carve-out costs the FFN-up / QKV GEMMs more (2.1 -> 2.2-3.1 ms);
+    // best setting (52 MB) 12.34 ms vs 12.28 ms without
+    const char* e = getenv("GAM_L2_PERSIST");
+    size_t want = static_cast<size_t>(prop.persistingL2CacheMaxSize);
+    const char* mb = getenv("GAM_L2_PERSIST_MB");
+    if (mb && atoi(mb) > 0 && static_cast<size_t>(atoi(mb)) * 1048576 < want) want = static_cast<size_t>(atoi(mb)) * 1048576;
+    if ((e && e[0] == '1') && prop.persistingL2CacheMaxSize > 0 &&
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
+      size_t got = 0;
+      cudaDeviceGetLimit(&got, cudaLimitPersistingL2CacheSize);
+      h->l2_persist_bytes = got;
+      h->l2_window_max = prop.accessPolicyMaxWindowSize;
+    }
+    cudaGetLastError();
+  }
   if (init_encode() != 0) return fail(h, -13, "cuTensorMapEncodeTiled entry point not available");
   if (gemm_init() != 0) return fail(h, -14, "cudaFuncSetAttribute failed for the GEMM kernels: %s", cudaGetErrorString(cudaGetLastError()));
   h->layers.assign(w->layers, w->layers + c.n_layers);
@@ -479,17 +499,30 @@ int gam_encode(gam_handle* h, const float* mel, const int64_t* mel_len, int32_t 
     launch_ln_f16(p->x, h->layers[0].ln_ff1_g, h->layers[0].ln_ff1_b, p->a16, R, s);
   }
   const int dk = d / c.n_heads;
+  // L2 residency window of the residual stream, attached only to the kernels that read / write x (launch.cuh)
+  L2Window xwin;
+  if (h->l2_persist_bytes > 0) {
+    const size_t xb = static_cast<size_t>(R) * d * sizeof(float);
+    xwin.base = p->x;
+    xwin.bytes = xb < h->l2_window_max ? xb : h->l2_window_max;
+    xwin.hit_ratio = xwin.bytes <= h->l2_persist_bytes ? 1.0f : static_cast<float>(h->l2_persist_bytes) / static_cast<float>(xwin.bytes);
+  }
+  struct WinScope {
+    explicit WinScope(const L2Window& w) { l2_window() = w; }
+    ~WinScope() { l2_window() = L2Window(); }
+  };
+#define XWIN WinScope win_scope__(xwin)
   for (int l = 0; l < L; ++l) {
     const gam_layer_weights& w = h->layers[l];
     const LayerMaps& m = h->lmaps[l];
     // x += 0.5 * FF1(LN(x))                                     (encoder.py:480-483)
     { PROF(PC_GEMM_FFN_UP);
       rc |= launch_gemm(GEMM_BIAS_SILU_F16, &p->m_a16, &m.ff1_w1, R, c.d_ff, d, w.ff1_b1, nullptr, p->big16, c.d_ff, 1.f, nsm, s); }
-    { PROF(PC_GEMM_FFN_DOWN);
+    { PROF(PC_GEMM_FFN_DOWN); XWIN;
       rc |= launch_gemm(GEMM_BIAS_RES_F32, &p->m_hid, &m.ff1_w2, R, d, c.d_ff, w.ff1_b2, p->x, p->x, d, 0.5f, nsm, s); }
     // x += W_o attn(q = W_q rope(u), k = W_k rope(u), v = W_v u), u = LN(x)   (encoder.py:485-487, 236-277)
     if (c.self_attention == 0) {
-      { PROF(PC_LAYERNORM);
+      { PROF(PC_LAYERNORM); XWIN;
         launch_ln_rope_f16(p->x, w.ln_att_g, w.ln_att_b, h->w.rope_cos, h->w.rope_sin, p->a16, p->r16, R, p->T2, dk / 2, s); }
       { PROF(PC_GEMM_QKV);
         rc |= launch_gemm(GEMM_BIAS_F16, &p->m_r16, &m.w_qk, R, 2 * d, d, w.b_qk, nullptr, p->big16, 3 * d, 1.f, nsm, s); }
@@ -499,17 +532,17 @@ int gam_encode(gam_handle* h, const float* mel, const int64_t* mel_len, int32_t 
         rc |= launch_attention(&p->m_qkv, B > 1 ? p->len2 : nullptr, p->o16, B, p->T2, c.n_heads, dk, d, s); }
     } else {
       // rel_pos (encoder.py:208-228): one projection GEMM -> [q+u | q+v | k | v], position scores inside the kernel
-      { PROF(PC_LAYERNORM);
+      { PROF(PC_LAYERNORM); XWIN;
         launch_ln_f16(p->x, w.ln_att_g, w.ln_att_b, p->a16, R, s); }
       { PROF(PC_GEMM_QKV);
         rc |= launch_gemm(GEMM_BIAS_F16, &p->m_a16, &m.w_qkv_rel, R, 4 * d, d, w.b_qkv_rel, nullptr, p->big16, 4 * d, 1.f, nsm, s); }
       { PROF(PC_ATTENTION);
         rc |= launch_attention_relpos(&p->m_qkv4, &m.pos_proj, B > 1 ? p->len2 : nullptr, p->o16, B, p->T2, c.n_heads, dk, d, s); }
     }
-    { PROF(PC_GEMM_PROJ);
+    { PROF(PC_GEMM_PROJ); XWIN;
       rc |= launch_gemm(GEMM_BIAS_RES_F32, &p->m_o16, &m.w_o, R, d, d, w.b_o, p->x, p->x, d, 1.f, nsm, s); }
     // x += Conv(LN(x))                                           (encoder.py:489-491, 396-409)
-    { PROF(PC_LAYERNORM);
+    { PROF(PC_LAYERNORM); XWIN;
       launch_ln_f16(p->x, w.ln_conv_g, w.ln_conv_b, p->a16, R, s); }
     { PROF(PC_GEMM_GLU);
       rc |= launch_gemm(GEMM_BIAS_GLU_F16, &p->m_a16, &m.pw1, R, 2 * d, d, w.pw1_b, nullptr, p->g16, d, 1.f, nsm, s); }
@@ -518,17 +551,17 @@ int gam_encode(gam_handle* h, const float* mel, const int64_t* mel_len, int32_t 
         rc |= launch_dwconv_bn_silu(p->g16, w.dw_w, w.dw_b, p->len2, p->o16, B, p->T2, c.conv_kernel_size, s);
       else
         rc |= launch_dwconv_ln_silu(p->g16, w.dw_w, w.dw_b, w.cn_g, w.cn_b, p->len2, p->o16, B, p->T2, c.conv_kernel_size, s); }
-    { PROF(PC_GEMM_PROJ);
+    { PROF(PC_GEMM_PROJ); XWIN;
       rc |= launch_gemm(GEMM_BIAS_RES_F32, &p->m_o16, &m.pw2, R, d, d, w.pw2_b, p->x, p->x, d, 1.f, nsm, s); }
     // x += 0.5 * FF2(LN(x))                                      (encoder.py:493-495)
-    { PROF(PC_LAYERNORM);
+    { PROF(PC_LAYERNORM); XWIN;
       launch_ln_f16(p->x, w.ln_ff2_g, w.ln_ff2_b, p->a16, R, s); }
     { PROF(PC_GEMM_FFN_UP);
       rc |= launch_gemm(GEMM_BIAS_SILU_F16, &p->m_a16, &m.ff2_w1, R, c.d_ff, d, w.ff2_b1, nullptr, p->big16, c.d_ff, 1.f, nsm, s); }
-    { PROF(PC_GEMM_FFN_DOWN);
+    { PROF(PC_GEMM_FFN_DOWN); XWIN;
       rc |= launch_gemm(GEMM_BIAS_RES_F32, &p->m_hid, &m.ff2_w2, R, d, c.d_ff, w.ff2_b2, p->x, p->x, d, 0.5f, nsm, s); }
     // x = LN_out(x) (+ next layer's first LN fused)                (encoder.py:497)
-    { PROF(PC_LAYERNORM);
+    { PROF(PC_LAYERNORM); XWIN;
       if (l + 1 < L)
         launch_ln_out_ln(p->x, w.ln_out_g, w.ln_out_b, h->layers[l + 1].ln_ff1_g, h->layers[l + 1].ln_ff1_b, p->x, p->a16, R, s);
       else

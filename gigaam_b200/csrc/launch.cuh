@@ -1,4 +1,4 @@
-// Kernel launch helper: programmatic dependent launch (PDL) on every kernel of the path.
+// Kernel launch helper: per-launch attributes of the path's kernels (L2 access-policy window, optional PDL).
 #pragma once
 #include <cuda_runtime.h>
 
@@ -18,8 +18,23 @@ inline bool pdl_enabled() {
   return v == 1;
 }
 
-// launch `kernel` so that it may start while its stream predecessor drains; the kernel itself calls
-// ptx::pdl_wait() before touching global memory (see ptx.cuh)
+// L2 residency window for the fp32 residual stream x [rows, d_model]: every layer reads and rewrites it eight times
+// (four residual GEMM epilogues, four LayerNorms), and at the benchmark shape it is 49 MB -- it fits the 126 MB L2
+// but is evicted by the weight / activation streams in between unless its lines are marked persisting.  The window
+// is a per-launch attribute, so it is recorded in CUDA-graph kernel nodes as well.  Set by gam_encode around the
+// layer loop; base == nullptr disables it.
+struct L2Window {
+  void* base = nullptr;
+  size_t bytes = 0;
+  float hit_ratio = 0.f;
+};
+inline L2Window& l2_window() {
+  static thread_local L2Window w;   // per host thread: handles driven from different threads do not interfere
+  return w;
+}
+
+// launch `kernel` with the path's launch attributes.  With PDL the kernel may start while its stream predecessor
+// drains; the kernel itself calls ptx::pdl_wait() before touching global memory (see ptx.cuh)
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
   cudaLaunchConfig_t cfg{};
@@ -27,11 +42,25 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute at[2];
+  int n = 0;
+  if (pdl_enabled()) {
+    at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  const L2Window& w = l2_window();
+  if (w.base != nullptr) {
+    at[n].id = cudaLaunchAttributeAccessPolicyWindow;
+    at[n].val.accessPolicyWindow.base_ptr = w.base;
+    at[n].val.accessPolicyWindow.num_bytes = w.bytes;
+    at[n].val.accessPolicyWindow.hitRatio = w.hit_ratio;
+    at[n].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    at[n].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    ++n;
+  }
   cfg.attrs = at;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = n;
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 

@@ -483,3 +483,25 @@ def test_v1_batch_vs_single_and_long(eng_v1):
     mel = eng_v1.logmel(wav.cuda())
     enc, enc_len = eng_v1.encode(mel, torch.tensor([mel.shape[2]]).cuda())
     assert int(enc_len[0]) == 626 and torch.isfinite(enc).all()
+
+
+# ------------------------------------------------------------------------------------------ serving loop
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_batch_pipeline_equals_direct_calls(dev, v2_ctc_ckpt, use_graph):
+    """gigaam_b200.pipeline.BatchPipeline (overlapped copies, CUDA-graph replay per shape) returns exactly what the
+    plain `model(wav, len)` + `model.decoding.decode(...)` calls return, batch after batch, across two shapes."""
+    from gigaam_b200.pipeline import BatchPipeline
+    model = gigaam.load_model("v2_ctc", device=dev, checkpoint=v2_ctc_ckpt)
+    batches = []
+    for i, (B, sec) in enumerate([(3, 2.0), (3, 2.0), (2, 3.0), (3, 2.0), (2, 3.0)]):
+        wav, wav_len = synthetic.synthetic_audio(B, sec, seed=100 + i, ragged=True)
+        batches.append((wav.pin_memory(), wav_len))
+    want = []
+    for wav, wav_len in batches:
+        enc, enc_len = model(wav.to(dev), wav_len.to(dev))
+        want.append(model.decoding.decode(model.head, enc, enc_len))
+    got = list(BatchPipeline(model, use_graph=use_graph).run(iter(batches)))
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        assert g == w
+    assert sum(len(h[1]) for hyps in want for h in hyps) > 0

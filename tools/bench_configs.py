@@ -16,6 +16,8 @@ CONFIGS = {
     "c1": ("v2_ctc", 1, 5.0), "c2": ("v2_ctc", 64, 10.0), "c3": ("v2_rnnt", 32, 15.0),
     "c4": ("v3_e2e_rnnt", 32, 10.0),   # per-GPU share of 256 x 10 s over 8 GPUs
     "c5": ("v2_ssl", 128, 25.0),
+    # not BASELINE configs: the rel_pos (v1) model on the c2 / c5 shapes
+    "v1c2": ("v1_ctc", 64, 10.0), "v1c5": ("v1_ssl", 128, 25.0),
 }
 
 
