@@ -219,6 +219,20 @@ __device__ __forceinline__ void cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// shared::cluster address of the shared::cta address `smem_addr` in CTA `cta` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(cta));
+  return r;
+}
+// 16-byte store into another CTA's shared memory whose arrival is counted (complete_tx, 16 bytes) on an mbarrier of
+// that same CTA: the receiver waits on its own barrier, no cluster-wide barrier / fence is involved
+__device__ __forceinline__ void st_async_v4(uint32_t remote_addr, uint32_t remote_bar, uint32_t a, uint32_t b, uint32_t c,
+                                            uint32_t d) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(remote_addr),
+               "r"(a), "r"(b), "r"(c), "r"(d), "r"(remote_bar)
+               : "memory");
+}
 // shared::cluster address of the same smem offset in the pair's leader (even-rank) CTA
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
 // arrive (count 1) on the mbarrier at the same smem offset in CTA `cta` of the cluster
