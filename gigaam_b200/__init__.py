@@ -22,10 +22,10 @@ import torch
 from .model import GigaAM, GigaAMASR
 from .preprocess import load_audio
 from .synthetic import synthetic_audio, synthetic_checkpoint
-from .types import TranscriptionResult, Word
+from .types import LongformTranscriptionResult, Segment, TranscriptionResult, Word
 
 __all__ = ["GigaAM", "GigaAMASR", "load_audio", "load_model", "synthetic_checkpoint", "synthetic_audio",
-           "TranscriptionResult", "Word"]
+           "TranscriptionResult", "Word", "Segment", "LongformTranscriptionResult"]
 
 _CACHE_DIR = os.path.expanduser("~/.cache/gigaam")
 _MODEL_NAMES = ["emo", "v1_ctc", "v1_rnnt", "v1_ssl", "v2_ctc", "v2_rnnt", "v2_ssl", "v3_ctc", "v3_rnnt",

@@ -171,6 +171,22 @@ class GigaAMASR(GigaAM):
         return TranscriptionResult(text=text, words=words)
 
     @torch.inference_mode()
+    def transcribe_longform(self, wav_file, word_timestamps: bool = False, fr_batch_size: int = 16, fr_num_workers: int = 0,
+                            segments: Optional[List[Tensor]] = None, boundaries: Optional[List[Tuple[float, float]]] = None,
+                            **kwargs):
+        """gigaam/model.py:195-259.  Segmentation is pluggable: pass `segments` / `boundaries` from any VAD (the
+        reference's pyannote pipeline, gigaam/vad_utils.py, is third party and not vendored); without them the
+        recording is cut at low-energy points (`longform.split_on_energy`, kwargs forwarded).  Segments are
+        length-bucketed into batches of `fr_batch_size`; `fr_num_workers` is accepted for signature compatibility."""
+        from .longform import split_on_energy, transcribe_segments
+        if segments is None:
+            wav = load_audio(wav_file) if isinstance(wav_file, str) else torch.as_tensor(wav_file, dtype=torch.float32).reshape(-1)
+            segments, boundaries = split_on_energy(wav, SAMPLE_RATE, **kwargs)
+        elif boundaries is None:
+            raise ValueError("boundaries are required when segments are given")
+        return transcribe_segments(self, segments, boundaries, word_timestamps, fr_batch_size)
+
+    @torch.inference_mode()
     def transcribe_batch(self, wav: Tensor, lengths: Tensor) -> List[str]:
         """Batched entry (the path eval.py / transcribe_longform drive: model(wav, len) -> decoding.decode)."""
         encoded, encoded_len = self.forward(wav, lengths)

@@ -280,6 +280,35 @@ def test_rnnt_edge_lengths(eng_rnnt, v2_rnnt_ckpt):
     assert int(counts[1]) == 0
 
 
+@pytest.mark.parametrize("which", ["v2", "v3"])
+def test_rnnt_batch_of_40_against_oracle_and_small_groups(which, eng_rnnt, v2_rnnt_ckpt, request):
+    """A batch too large for one 4-utterance group per cluster takes the 8-utterance kernel variant (two float4 halves,
+    ragged last group); it must give the oracle's hypotheses and exactly what the 4-utterance variant gives when the
+    same utterances are decoded in batches of 3.  v3 = 1025 classes: part of W_o stays in L2 (the prefetch path)."""
+    if which == "v2":
+        eng, sd = eng_rnnt, v2_rnnt_ckpt["state_dict"]
+    else:
+        eng, sd = request.getfixturevalue("eng_v3"), request.getfixturevalue("v3_ckpt")["state_dict"]
+    g = torch.Generator().manual_seed(21)
+    B, T = 40, 24
+    enc = torch.randn(B, T, 768, generator=g) * 0.5
+    enc_len = torch.randint(0, T + 1, (B,), generator=g, dtype=torch.int32)
+    enc_len[0], enc_len[7] = T, 0
+    ids, frames, counts = (x.cpu() for x in eng.greedy(enc.cuda(), enc_len.cuda()))
+    want = orc.rnnt_greedy(enc[:12].transpose(1, 2), enc_len[:12], sd, 10)
+    for b in range(12):
+        n = int(counts[b])
+        assert ids[b, :n].tolist() == want[b][0] and frames[b, :n].tolist() == want[b][1], b
+    for b0 in range(0, B, 3):
+        i3, f3, c3 = (x.cpu() for x in eng.greedy(enc[b0:b0 + 3].contiguous().cuda(), enc_len[b0:b0 + 3].cuda()))
+        for j in range(min(3, B - b0)):
+            n = int(c3[j])
+            assert n == int(counts[b0 + j])
+            assert torch.equal(i3[j, :n], ids[b0 + j, :n]) and torch.equal(f3[j, :n], frames[b0 + j, :n])
+    if which == "v2":
+        assert int(counts.sum()) > 0
+
+
 # ------------------------------------------------------------------------------------------ public API (drop-in surface)
 def test_public_api_drop_in(dev, v2_ctc_ckpt):
     model = gigaam.load_model("v2_ctc", device=dev, checkpoint=v2_ctc_ckpt)     # reference default: fp16 encoder
@@ -505,3 +534,36 @@ def test_batch_pipeline_equals_direct_calls(dev, v2_ctc_ckpt, use_graph):
     for g, w in zip(got, want):
         assert g == w
     assert sum(len(h[1]) for hyps in want for h in hyps) > 0
+
+
+def test_transcribe_longform_equals_per_segment_transcribe(dev, v2_ctc_ckpt):
+    """transcribe_longform (gigaam/model.py:195-259) over pre-cut segments == transcribe() of every segment alone, in
+    recording order, with word timestamps shifted by the segment start; the built-in splitter handles a 50 s waveform
+    that transcribe() itself refuses (>25 s, model.py:135-136)."""
+    model = gigaam.load_model("v2_ctc", device=dev, checkpoint=v2_ctc_ckpt)
+    wavs, lens = synthetic.synthetic_audio(5, 4.0, seed=77, ragged=True)
+    segments = [wavs[i, : int(lens[i])] for i in range(5)]
+    bounds, t0 = [], 0.0
+    for s in segments:
+        bounds.append((t0, t0 + s.numel() / 16000.0))
+        t0 += s.numel() / 16000.0 + 0.5
+    res = model.transcribe_longform(None, word_timestamps=True, fr_batch_size=1, segments=segments, boundaries=bounds)
+    assert isinstance(res, gigaam.LongformTranscriptionResult) and len(res) == 5 and res.has_word_timestamps
+    alone = [model.transcribe(wav, word_timestamps=True) for wav in segments]
+    for seg, one, (s0, e0) in zip(res, alone, bounds):
+        assert seg.text == one.text and (seg.start, seg.end) == (s0, e0)
+        assert [w.text for w in seg.words] == [w.text for w in one.words]
+        for a, b in zip(seg.words, one.words):
+            assert a.start == pytest.approx(b.start + s0, abs=2e-3) and a.end == pytest.approx(b.end + s0, abs=2e-3)
+    # length-bucketed batches of 2: the padded member's last mel frames see zeros instead of the reflection a lone run
+    # sees (same as the reference's padded batches), so only its tail may differ
+    res2 = model.transcribe_longform(None, fr_batch_size=2, segments=segments, boundaries=bounds)
+    assert len(res2) == 5 and not res2.has_word_timestamps
+    for seg, one, (s0, e0) in zip(res2, alone, bounds):
+        assert (seg.start, seg.end) == (s0, e0) and seg.text[:-3] == one.text[: len(seg.text[:-3])]
+    long_wav, _ = synthetic.synthetic_audio(1, 50.0, seed=78)
+    with pytest.raises(ValueError):
+        model.transcribe(long_wav[0])
+    res = model.transcribe_longform(long_wav[0])
+    assert len(res) >= 3 and res.segments[0].start == 0.0 and res.segments[-1].end == pytest.approx(50.0)
+    assert all(s.end - s.start <= 22.0 + 1e-6 for s in res) and isinstance(res.text, str)

@@ -185,3 +185,32 @@ def test_synthetic_audio_is_deterministic_and_bounded():
 def test_transcription_result_str():
     r = gigaam.TranscriptionResult(text="привет")
     assert str(r) == "привет" and r.words is None
+
+
+def test_longform_result_type_and_batch_planning():
+    """Host side of transcribe_longform (gigaam/model.py:195-259, gigaam/types.py:38-67): result helpers, length
+    bucketing (every segment exactly once, batches bounded, less padding than arrival order) and the energy splitter."""
+    from gigaam_b200.longform import padding_waste, plan_batches, split_on_energy
+    segs = [gigaam.Segment("a b", 0.0, 1.0, [gigaam.Word("a", 0.1, 0.2), gigaam.Word("b", 0.3, 0.4)]), gigaam.Segment("c", 1.0, 2.0, [])]
+    res = gigaam.LongformTranscriptionResult(segments=segs)
+    assert str(res) == res.text == "a b c" and len(res) == 2 and [s.text for s in res] == ["a b", "c"]
+    assert res.has_word_timestamps and [w.text for w in res.words] == ["a", "b"]
+    assert not gigaam.LongformTranscriptionResult(segments=[]).has_word_timestamps
+    gen = torch.Generator().manual_seed(3)
+    lengths = torch.randint(8000, 352000, (37,), generator=gen).tolist()
+    batches = plan_batches(lengths, 8)
+    assert sorted(i for b in batches for i in b) == list(range(37)) and max(len(b) for b in batches) == 8 and len(batches) == 5
+    arrival = [list(range(i, min(i + 8, 37))) for i in range(0, 37, 8)]
+    assert padding_waste(lengths, batches) < 0.5 * padding_waste(lengths, arrival)
+    with pytest.raises(ValueError):
+        plan_batches(lengths, 0)
+    # 60 s: loud / quiet alternation every 10 s -> cuts land inside quiet stretches, every piece <= 22 s, nothing lost
+    t = torch.arange(60 * 16000) / 16000.0
+    loud = ((t // 10) % 2 == 0).float()
+    wav = torch.sin(2 * torch.pi * 220 * t) * (0.5 * loud + 0.001)
+    pieces, bounds = split_on_energy(wav)
+    assert sum(p.numel() for p in pieces) == wav.numel() and torch.equal(torch.cat(pieces), wav)
+    assert all(p.numel() <= 22 * 16000 for p in pieces) and len(pieces) == len(bounds) >= 3
+    assert bounds[0][0] == 0.0 and bounds[-1][1] == pytest.approx(60.0)
+    for (s0, e0), (s1, _) in zip(bounds, bounds[1:]):
+        assert e0 == s1 and loud[int(e0 * 16000)] == 0.0
