@@ -136,8 +136,7 @@ __device__ long long g_rnnt_dbg[16];
 #endif
 
 // NH: float4 halves of utterances per group (4 or 8 utterances).  GLOB: some class rows stay in L2 (large vocabularies);
-// compiled out otherwise -- the round loop is executed once per step by every warp, and its code footprint already
-// exceeds the 32 KB instruction cache, so every instruction that is not needed costs fetch time.
+// compiled out otherwise (the round loop is executed once per step by every warp; 16 KB less code).
 template <int NH, bool GLOB>
 __global__ void __launch_bounds__(kThreads, 1) rnnt_cluster_kernel(const RnntClParams p) {
   constexpr int NU = 4 * NH;
