@@ -187,6 +187,41 @@ def test_transcription_result_str():
     assert str(r) == "привет" and r.words is None
 
 
+def test_rel_pos_weight_packing_reproduces_the_reference_scores():
+    """The load-time re-layout of the rel_pos attention (engine.pack_rel_pos_qkv, engine.rel_pos_embedding, pos_proj) in
+    fp32 on the CPU: one projection [q+u | q+v | k | v], position rows read from the fixed 2*640-1 table at
+    REL_POS_MAX_T-1-(i-j), must give the oracle's RelPositionMultiHeadAttention (gigaam/encoder.py:208-228)."""
+    from oracle import gigaam_oracle as orc
+    torch.manual_seed(5)
+    d, H, T, B = 768, 16, 37, 2
+    dk, L = d // H, _lib.REL_POS_MAX_T
+    q = "a."
+    sd = {q + f"linear_{n}.weight": torch.randn(d, d) / d ** 0.5 for n in ("q", "k", "v", "out", "pos")}
+    sd.update({q + f"linear_{n}.bias": torch.randn(d) * 0.1 for n in ("q", "k", "v", "out")})
+    sd[q + "pos_bias_u"], sd[q + "pos_bias_v"] = torch.randn(H, dk) * 0.2, torch.randn(H, dk) * 0.2
+    x = torch.randn(B, T, d)
+    key_valid = torch.arange(T)[None, :] < torch.tensor([T, 20])[:, None]
+    want = orc.rel_pos_mhsa(x, sd, q, H, orc.rel_pos_table(T, d), key_valid)
+    # the engine's packing
+    w4, b4 = engine.pack_rel_pos_qkv(sd[q + "linear_q.weight"], sd[q + "linear_q.bias"], sd[q + "linear_k.weight"], sd[q + "linear_k.bias"],
+                                     sd[q + "linear_v.weight"], sd[q + "linear_v.bias"], sd[q + "pos_bias_u"], sd[q + "pos_bias_v"])
+    assert w4.shape == (4 * d, d) and b4.shape == (4 * d,)
+    pe = engine.rel_pos_embedding(L, d)
+    assert pe.shape == (2 * L - 1, d) and torch.equal(pe[L - T: L + T - 1], orc.rel_pos_table(T, d))
+    pos_proj = pe @ sd[q + "linear_pos.weight"].t()
+    qkv = (x @ w4.t() + b4).view(B, T, 4, H, dk)
+    qu, qv, k, v = (qkv[:, :, i].transpose(1, 2) for i in range(4))
+    p = pos_proj.view(2 * L - 1, H, dk).transpose(0, 1)                      # [H, 2L-1, dk]
+    row = (L - 1) - (torch.arange(T)[:, None] - torch.arange(T)[None, :])     # table row of relative position i - j
+    bd = torch.einsum("bhid,hijd->bhij", qv, p[:, row])                        # what the kernel's skewed window MMA computes
+    sc = (qu @ k.transpose(-1, -2) + bd) / dk ** 0.5
+    sc = sc.masked_fill(~key_valid[:, None, None, :], float("-inf"))
+    o = (torch.softmax(sc, -1) @ v).transpose(1, 2).reshape(B, T, d)
+    got = F.linear(o, sd[q + "linear_out.weight"], sd[q + "linear_out.bias"])
+    valid_q = key_valid
+    assert float((got[valid_q] - want[valid_q]).abs().max()) < 2e-4
+
+
 def test_longform_result_type_and_batch_planning():
     """Host side of transcribe_longform (gigaam/model.py:195-259, gigaam/types.py:38-67): result helpers, length
     bucketing (every segment exactly once, batches bounded, less padding than arrival order) and the energy splitter."""
