@@ -280,17 +280,18 @@ def test_rnnt_edge_lengths(eng_rnnt, v2_rnnt_ckpt):
     assert int(counts[1]) == 0
 
 
-@pytest.mark.parametrize("which", ["v2", "v3"])
-def test_rnnt_batch_of_40_against_oracle_and_small_groups(which, eng_rnnt, v2_rnnt_ckpt, request):
+@pytest.mark.parametrize("which,B", [("v2", 40), ("v3", 40), ("v2", 61)])
+def test_rnnt_large_batches_against_oracle_and_small_groups(which, B, eng_rnnt, v2_rnnt_ckpt, request):
     """A batch too large for one 4-utterance group per cluster takes the 8-utterance kernel variant (two float4 halves,
     ragged last group); it must give the oracle's hypotheses and exactly what the 4-utterance variant gives when the
-    same utterances are decoded in batches of 3.  v3 = 1025 classes: part of W_o stays in L2 (the prefetch path)."""
+    same utterances are decoded in batches of 3.  v3 = 1025 classes: part of W_o stays in L2 (the prefetch path).
+    B = 61 needs more groups than clusters can be resident (7 on a B200): clusters decode a second group after their first."""
     if which == "v2":
         eng, sd = eng_rnnt, v2_rnnt_ckpt["state_dict"]
     else:
         eng, sd = request.getfixturevalue("eng_v3"), request.getfixturevalue("v3_ckpt")["state_dict"]
     g = torch.Generator().manual_seed(21)
-    B, T = 40, 24
+    T = 24
     enc = torch.randn(B, T, 768, generator=g) * 0.5
     enc_len = torch.randint(0, T + 1, (B,), generator=g, dtype=torch.int32)
     enc_len[0], enc_len[7] = T, 0
