@@ -77,6 +77,8 @@ static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * 
 struct LayerMaps {
   CUtensorMap ff1_w1, ff1_w2, w_qk, w_v, w_o, pw1, pw2, ff2_w1, ff2_w2;
   CUtensorMap w_qkv_rel, pos_proj;   // rel_pos attention only
+  CUtensorMap w_qkv;                 // rotary: [W_q ; W_k ; W_v] when the caller packed them contiguously
+  bool qkv_merged = false;
 };
 
 struct Plan {
@@ -326,6 +328,9 @@ int gam_create(const gam_config* cfg, const gam_weights* w, int device, gam_hand
     if (c.self_attention == 0) {
       rc |= make_tmap_2d_f16(&lm.w_qk, lw.w_qk, 2 * d, d, d, 128, 64);
       rc |= make_tmap_2d_f16(&lm.w_v, lw.w_v, d, d, d, 128, 64);
+      // W_v directly behind W_qk (and b_v behind b_qk): q, k and v projections run as one launch (launch_gemm_dual_a)
+      lm.qkv_merged = static_cast<const char*>(lw.w_v) == static_cast<const char*>(lw.w_qk) + 2 * d * d * 2 && lw.b_v == lw.b_qk + 2 * d;
+      if (lm.qkv_merged) rc |= make_tmap_2d_f16(&lm.w_qkv, lw.w_qk, 3 * d, d, d, 128, 64);
     } else {
       if (!lw.w_qkv_rel || !lw.b_qkv_rel || !lw.pos_proj) return fail(h, -10, "layer %d: rel_pos weights missing", l);
       rc |= make_tmap_2d_f16(&lm.w_qkv_rel, lw.w_qkv_rel, 4 * d, d, d, 128, 64);
@@ -524,10 +529,17 @@ int gam_encode(gam_handle* h, const float* mel, const int64_t* mel_len, int32_t 
     if (c.self_attention == 0) {
       { PROF(PC_LAYERNORM); XWIN;
         launch_ln_rope_f16(p->x, w.ln_att_g, w.ln_att_b, h->w.rope_cos, h->w.rope_sin, p->a16, p->r16, R, p->T2, dk / 2, s); }
-      { PROF(PC_GEMM_QKV);
-        rc |= launch_gemm(GEMM_BIAS_F16, &p->m_r16, &m.w_qk, R, 2 * d, d, w.b_qk, nullptr, p->big16, 3 * d, 1.f, nsm, s); }
-      { PROF(PC_GEMM_QKV);
-        rc |= launch_gemm(GEMM_BIAS_F16, &p->m_a16, &m.w_v, R, d, d, w.b_v, nullptr, p->big16 + 2 * d, 3 * d, 1.f, nsm, s); }
+      bool merged = false;
+      if (m.qkv_merged) {
+        PROF(PC_GEMM_QKV);
+        merged = launch_gemm_dual_a(&p->m_r16, &p->m_a16, 2 * d, &m.w_qkv, R, 3 * d, d, w.b_qk, p->big16, 3 * d, nsm, s) == 0;
+      }
+      if (!merged) {
+        { PROF(PC_GEMM_QKV);
+          rc |= launch_gemm(GEMM_BIAS_F16, &p->m_r16, &m.w_qk, R, 2 * d, d, w.b_qk, nullptr, p->big16, 3 * d, 1.f, nsm, s); }
+        { PROF(PC_GEMM_QKV);
+          rc |= launch_gemm(GEMM_BIAS_F16, &p->m_a16, &m.w_v, R, d, d, w.b_v, nullptr, p->big16 + 2 * d, 3 * d, 1.f, nsm, s); }
+      }
       { PROF(PC_ATTENTION);
         rc |= launch_attention(&p->m_qkv, B > 1 ? p->len2 : nullptr, p->o16, B, p->T2, c.n_heads, dk, d, s); }
     } else {

@@ -32,14 +32,15 @@ int launch_v1(const CUtensorMap* ta, const CUtensorMap* tw, const GemmParams& p,
 
 // p.num_m_tiles counts 128-row blocks on entry; the pair kernel wants 256-row pair tiles
 template <int EPI, int AMODE>
-int launch_v2(const CUtensorMap* ta, const CUtensorMap* tw, GemmParams p, int num_sms, cudaStream_t s) {
+int launch_v2(const CUtensorMap* ta, const CUtensorMap* tw, GemmParams p, int num_sms, cudaStream_t s,
+              const CUtensorMap* ta2 = nullptr) {
   auto kern = gemm2_f16_tn_kernel<EPI, AMODE>;
   p.num_m_tiles = (p.num_m_tiles + 1) / 2;
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int max_pairs = num_sms / 2;
   const int npairs = tiles < max_pairs ? tiles : max_pairs;
   if (npairs <= 0) return 0;
-  return launch_pdl(kern, dim3(2 * npairs), dim3(kG2Threads), kG2Smem, s, *ta, *tw, p) == cudaSuccess ? 0 : -2;
+  return launch_pdl(kern, dim3(2 * npairs), dim3(kG2Threads), kG2Smem, s, *ta, ta2 ? *ta2 : *ta, *tw, p) == cudaSuccess ? 0 : -2;
 }
 
 template <int EPI, int AMODE>
@@ -91,6 +92,25 @@ int launch_gemm(int kind, const CUtensorMap* ta, const CUtensorMap* tw, int M, i
     case GEMM_BIAS_F32: return launch_one<EPI_BIAS_F32, A_2D>(ta, tw, p, num_sms, s);
     default: return -1;
   }
+}
+
+// D[:, :n1] = A1 W[:n1]^T + b, D[:, n1:] = A2 W[n1:]^T + b  (fp16 out) in ONE launch of the pair kernel: more tiles per
+// launch = less wave quantisation (QK + V: 378 + 189 tiles on 74 pairs = 6 + 3 waves apart, 8 together) and one launch less.
+int launch_gemm_dual_a(const CUtensorMap* ta1, const CUtensorMap* ta2, int n1, const CUtensorMap* tw, int M, int N, int K,
+                       const float* bias, void* out, int ldo, int num_sms, cudaStream_t s) {
+  if (N % kBN != 0 || n1 % kBN != 0 || n1 <= 0 || n1 >= N || K % kGemmBK != 0 || M <= 0 || use_v1()) return -1;
+  GemmParams p{};
+  p.M = M;
+  p.N = N;
+  p.num_m_tiles = (M + kGemmBM - 1) / kGemmBM;
+  p.num_n_tiles = N / kBN;
+  p.num_k_blocks = K / kGemmBK;
+  p.bias = bias;
+  p.out = out;
+  p.ldo = ldo;
+  p.scale = 1.f;
+  p.a1_nblks = n1 / kBN;
+  return launch_v2<EPI_BIAS_F16, A_2D>(ta1, tw, p, num_sms, s, ta2);
 }
 
 int launch_gemm_conv(const CUtensorMap* ta4, const CUtensorMap* tw, int B, int T2, int C, int N, const float* bias,

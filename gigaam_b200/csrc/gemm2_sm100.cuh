@@ -37,8 +37,8 @@ constexpr int kG2Smem = kG2Stages * kG2StageBytes + kG2EpiBytes + kG2BarBytes + 
 
 template <int EPI, int AMODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kG2Threads, 1)
-gemm2_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
-                    const GemmParams p) {
+gemm2_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a2,
+                    const __grid_constant__ CUtensorMap tmap_w, const GemmParams p) {
   constexpr int BN = 256;
   constexpr uint32_t kTmemCols = 512;
   constexpr uint32_t kIdesc = ptx::make_idesc_f16(256, BN, 0, 0);
@@ -65,6 +65,7 @@ gemm2_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
   if (warp_idx == 0 && ptx::elect_one()) {
     ptx::prefetch_tmap(&tmap_a);
+    ptx::prefetch_tmap(&tmap_a2);
     ptx::prefetch_tmap(&tmap_w);
     for (int s = 0; s < kG2Stages; ++s) {
       ptx::mbar_init(&full_bar[s], 2);   // one arrival per CTA's producer (+ the transaction bytes of both)
@@ -93,6 +94,7 @@ gemm2_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const int m_pair = tile / p.num_n_tiles;
         const int n_blk = tile % p.num_n_tiles;
         const int m_blk = m_pair * 2 + static_cast<int>(rank);   // this CTA's 128-row block
+        const CUtensorMap* ta = (p.a1_nblks > 0 && n_blk >= p.a1_nblks) ? &tmap_a2 : &tmap_a;
         int conv_b = 0, conv_t0 = 0;
         if constexpr (AMODE == A_CONV) {
           conv_b = m_blk / p.conv_tiles_per_utt;   // == B for the idle block of an odd count: OOB -> zero fill
@@ -107,7 +109,7 @@ gemm2_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * kG2StageBytes);
           else ptx::mbar_arrive_cluster(&full_bar[stage], 0);
           if constexpr (AMODE == A_2D) {
-            ptx::tma_load_2d_2sm(smem_a + stage * kG2ABytes, &tmap_a, &full_bar[stage], kb * kGemmBK, m_blk * 128);
+            ptx::tma_load_2d_2sm(smem_a + stage * kG2ABytes, ta, &full_bar[stage], kb * kGemmBK, m_blk * 128);
           } else if constexpr (AMODE == A_CONV1D) {
             const int tap = kb / p.conv_kchunks;
             const int c0 = (kb % p.conv_kchunks) * kGemmBK;

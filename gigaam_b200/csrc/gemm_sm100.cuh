@@ -51,6 +51,9 @@ struct GemmParams {
   int conv_num_blocks;    // B * conv_tiles_per_utt  (128-row blocks that exist)
   int conv_pad;           // A_CONV1D: (taps - 1) / 2
   const int* conv_len2;   // [B] valid output time steps
+  // pair kernel, A_2D only: n-tiles [0, a1_nblks) read A through tmap_a, the rest through tmap_a2 (0 = tmap_a for all).
+  // Lets two GEMMs that share M, K and the output buffer but not the A operand (W_qk on rope(u), W_v on u) run as one launch.
+  int a1_nblks;
 };
 
 constexpr int kGemmBM = 128;

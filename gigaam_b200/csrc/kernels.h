@@ -67,6 +67,10 @@ enum GemmKind : int {
 // 2-D operand GEMM  D[M,N] = A[M,K] W[N,K]^T with fused epilogue `kind`; N % 256 == 0, K % 64 == 0.
 int launch_gemm(int kind, const CUtensorMap* tmap_a, const CUtensorMap* tmap_w, int M, int N, int K, const float* bias,
                 const float* res, void* out, int ldo, float scale, int num_sms, cudaStream_t s);
+// one launch for two GEMMs that share M, K, W's row space and the output buffer but read different A operands:
+// columns [0, n1) from tmap_a1, [n1, N) from tmap_a2 (bias -> fp16).  Returns -1 when the single-CTA kernel is forced.
+int launch_gemm_dual_a(const CUtensorMap* tmap_a1, const CUtensorMap* tmap_a2, int n1, const CUtensorMap* tmap_w, int M, int N,
+                       int K, const float* bias, void* out, int ldo, int num_sms, cudaStream_t s);
 // implicit-GEMM 3x3/s2 conv over channels-last [B,T1,F1,C] (tmap_a 4-D strided), output [B*T2*16, N] fp16
 int launch_gemm_conv(const CUtensorMap* tmap_a4d, const CUtensorMap* tmap_w, int B, int T2, int C, int N, const float* bias,
                      const int* len2, void* out, int ldo, int num_sms, cudaStream_t s);

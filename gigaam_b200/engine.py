@@ -244,9 +244,13 @@ class Engine:
             lw.pos_proj = self._dev(self._pos_emb @ f("self_attn.linear_pos.weight").to(self.device).t(), h16)
             lw.w_qk = lw.b_qk = lw.w_v = lw.b_v = None
         else:
-            lw.w_qk = self._dev(torch.cat([f("self_attn.linear_q.weight"), f("self_attn.linear_k.weight")], 0), h16)
-            lw.b_qk = self._dev(torch.cat([f("self_attn.linear_q.bias"), f("self_attn.linear_k.bias")], 0))
-            lw.w_v, lw.b_v = self._dev(f("self_attn.linear_v.weight"), h16), self._dev(f("self_attn.linear_v.bias"))
+            # [W_q ; W_k ; W_v] and their biases in ONE allocation each: w_v / b_v point behind w_qk / b_qk, which lets the
+            # library run the three projections as a single launch (two A operands: rope(u) for q, k and u for v)
+            w_qkv = self._dev(torch.cat([f("self_attn.linear_q.weight"), f("self_attn.linear_k.weight"),
+                                         f("self_attn.linear_v.weight")], 0), h16)
+            b_qkv = self._dev(torch.cat([f("self_attn.linear_q.bias"), f("self_attn.linear_k.bias"), f("self_attn.linear_v.bias")], 0))
+            lw.w_qk, lw.w_v = w_qkv, w_qkv + 2 * d * d * 2
+            lw.b_qk, lw.b_v = b_qkv, b_qkv + 2 * d * 4
             lw.w_qkv_rel = lw.b_qkv_rel = lw.pos_proj = None
         lw.w_o, lw.b_o = self._dev(f("self_attn.linear_out.weight"), h16), self._dev(f("self_attn.linear_out.bias"))
         lw.ln_conv_g, lw.ln_conv_b = self._dev(f("norm_conv.weight")), self._dev(f("norm_conv.bias"))

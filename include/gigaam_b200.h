@@ -55,7 +55,8 @@ typedef struct gam_layer_weights {
   const float *ln_att_g, *ln_att_b;
   const void* w_qk; /* h [2d, d] = [linear_q ; linear_k] */
   const float* b_qk;
-  const void* w_v; /* h [d, d] */
+  const void* w_v; /* h [d, d].  When w_v sits directly behind w_qk (one [3d, d] matrix) and b_v directly behind b_qk, the
+                    * q, k and v projections run as a single launch */
   const float* b_v;
   const void* w_o; /* h [d, d] */
   const float* b_o;
