@@ -187,6 +187,28 @@ def test_transcription_result_str():
     assert str(r) == "привет" and r.words is None
 
 
+def test_bench_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference` (the CPU oracle port timed on the host cores) must print exactly one JSON line on stdout
+    with the keys the driver reads, also when launched as a non-zero rank (which stays silent)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    cmd = [sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=str(ROOT))
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "utt/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "utt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and d["metric"].startswith("utterances/sec")
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=str(ROOT), env=env)
+    assert out.returncode == 0 and out.stdout.strip() == ""
+
+
 def test_rel_pos_weight_packing_reproduces_the_reference_scores():
     """The load-time re-layout of the rel_pos attention (engine.pack_rel_pos_qkv, engine.rel_pos_embedding, pos_proj) in
     fp32 on the CPU: one projection [q+u | q+v | k | v], position rows read from the fixed 2*640-1 table at
