@@ -352,7 +352,8 @@ def main():
                     "classes_ms_per_step": {k: round(v[0] / nprof, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}}
 
     if rank == 0:
-        cpu = None if args.no_cpu_baseline else cpu_reference(steps=2, warmup=1)
+        # the CPU baseline is a property of the box, not of N: timed at N = 1 only (other ranks would idle behind it)
+        cpu = None if (args.no_cpu_baseline or world > 1) else cpu_reference(steps=2, warmup=1)
         line = {"metric": "utterances/sec (10 s audio, v2_ctc)", "value": value, "unit": "utt/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f16 tensor-core operands, f32 accumulate/residual/norm/head",
