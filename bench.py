@@ -101,7 +101,7 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference(steps: int, warmup: int, batch: int = 4, seconds: float = SECONDS):
+def cpu_reference(steps: int, warmup: int, batch: int = 16, seconds: float = SECONDS):
     """The reference's CPU PyTorch path restated (oracle/gigaam_oracle.py: same ATen ops, fp32, no autocast --
     gigaam/model.py:34-35) on all host cores: log-mel + encoder + CTC greedy incl. host detokenisation."""
     import torch
@@ -353,7 +353,7 @@ def main():
 
     if rank == 0:
         # the CPU baseline is a property of the box, not of N: timed at N = 1 only (other ranks would idle behind it)
-        cpu = None if (args.no_cpu_baseline or world > 1) else cpu_reference(steps=2, warmup=1)
+        cpu = None if (args.no_cpu_baseline or world > 1) else cpu_reference(steps=3, warmup=1)   # ~12 s of CPU work
         line = {"metric": "utterances/sec (10 s audio, v2_ctc)", "value": value, "unit": "utt/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f16 tensor-core operands, f32 accumulate/residual/norm/head",
