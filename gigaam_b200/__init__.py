@@ -12,9 +12,6 @@ from __future__ import annotations
 import hashlib
 import logging
 import os
-import sys
-import types
-import warnings
 from typing import Dict, Optional, Union
 
 import torch
@@ -40,27 +37,10 @@ def _normalize_device(device: Optional[Union[str, torch.device]]) -> torch.devic
 
 
 def _torch_load_ckpt(path: str) -> Dict:
-    """Reference checkpoints pickle an omegaconf.DictConfig; when omegaconf is not installed a minimal stand-in
-    module lets the unpickler rebuild it as plain containers."""
-    try:
-        import omegaconf  # noqa: F401
-    except Exception:
-        stub = types.ModuleType("omegaconf")
-
-        class _Cfg(dict):
-            def __setstate__(self, state):
-                content = state.get("_content", state) if isinstance(state, dict) else {}
-                for k, v in (content.items() if hasattr(content, "items") else []):
-                    self[k] = getattr(v, "_val", v)
-
-            __getattr__ = dict.get
-
-        stub.DictConfig = _Cfg
-        stub.ListConfig = list
-        sys.modules.setdefault("omegaconf", stub)
-    with warnings.catch_warnings():
-        warnings.simplefilter("ignore", category=FutureWarning)
-        return torch.load(path, map_location="cpu", weights_only=False)
+    """Reference checkpoints pickle an omegaconf.DictConfig as their cfg; `ckpt.load_checkpoint` reads them with or
+    without omegaconf installed."""
+    from .ckpt import load_checkpoint
+    return load_checkpoint(path)
 
 
 def load_model(model_name: str, fp16_encoder: bool = True, use_flash: Optional[bool] = False,

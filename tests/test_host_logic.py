@@ -187,6 +187,67 @@ def test_transcription_result_str():
     assert str(r) == "привет" and r.words is None
 
 
+def test_checkpoint_with_omegaconf_cfg_loads_without_omegaconf(tmp_path):
+    """A reference `.ckpt` pickles its cfg as omegaconf objects (gigaam/__init__.py:167).  Build a pickle with the same
+    shape from throw-away classes registered under the omegaconf module names, drop those modules, and read it back with
+    gigaam_b200.ckpt: plain containers with the values, tensors intact, and `load_model(<path>)`-style use works."""
+    import sys
+    import types as pytypes
+    from gigaam_b200 import ckpt
+    if "omegaconf" in sys.modules and not isinstance(sys.modules["omegaconf"], pytypes.ModuleType):
+        pytest.skip("unexpected omegaconf module object")
+    try:
+        import omegaconf  # noqa: F401
+        pytest.skip("omegaconf is installed: the ordinary torch.load path is used")
+    except ImportError:
+        pass
+    names = {"omegaconf": [], "omegaconf.base": ["ContainerMetadata", "NodeMetadata"], "omegaconf.dictconfig": ["DictConfig"],
+             "omegaconf.listconfig": ["ListConfig"], "omegaconf.nodes": ["AnyNode", "StringNode", "IntegerNode"]}
+    mods, cls = {}, {}
+    for mod, classes in names.items():
+        m = pytypes.ModuleType(mod)
+        for c in classes:
+            k = type(c, (), {})
+            k.__module__ = mod
+            setattr(m, c, k)
+            cls[c] = k
+        mods[mod] = m
+
+    def node(kind, val, parent=None):
+        n = cls[kind]()
+        n.__dict__.update(_val=val, _parent=parent, _flags_cache=None)
+        meta = cls["NodeMetadata"]()
+        meta.__dict__.update(ref_type=object, object_type=None, optional=True, key=None, flags=None)
+        n.__dict__["_metadata"] = meta
+        return n
+
+    def container(kind, content):
+        c = cls[kind]()
+        meta = cls["ContainerMetadata"]()
+        meta.__dict__.update(ref_type=object, object_type=dict, optional=True, key=None, flags={}, key_type=str, element_type=object)
+        c.__dict__.update(_metadata=meta, _parent=None, _flags_cache=None, _content=content)
+        return c
+
+    enc = container("DictConfig", {"_target_": node("StringNode", "gigaam.encoder.ConformerEncoder"), "n_layers": node("IntegerNode", 16),
+                                   "subsampling": node("AnyNode", "conv2d")})
+    vocab = container("ListConfig", [node("StringNode", " "), node("StringNode", "а")])
+    cfg = container("DictConfig", {"model_name": node("StringNode", "v2_ctc"), "encoder": enc,
+                                   "decoding": container("DictConfig", {"vocabulary": vocab})})
+    path = tmp_path / "fake.ckpt"
+    sys.modules.update(mods)
+    try:
+        torch.save({"cfg": cfg, "state_dict": {"w": torch.arange(6.0).view(2, 3)}}, path)
+    finally:
+        for mod in mods:
+            sys.modules.pop(mod, None)
+    got = ckpt.load_checkpoint(str(path))
+    assert got["cfg"] == {"model_name": "v2_ctc",
+                          "encoder": {"_target_": "gigaam.encoder.ConformerEncoder", "n_layers": 16, "subsampling": "conv2d"},
+                          "decoding": {"vocabulary": [" ", "а"]}}
+    assert torch.equal(got["state_dict"]["w"], torch.arange(6.0).view(2, 3))
+    assert gigaam._torch_load_ckpt(str(path))["cfg"]["encoder"]["n_layers"] == 16
+
+
 def test_bench_reference_arm_prints_one_contract_line():
     """`bench.py --impl reference` (the CPU oracle port timed on the host cores) must print exactly one JSON line on stdout
     with the keys the driver reads, also when launched as a non-zero rank (which stays silent)."""
