@@ -20,6 +20,7 @@
 //   warp 1    : MMA   - S = Qu K^T  (TMEM cols 0..127), BD = Qv Pw^T (cols 256..511), O += P V (cols 128..191)
 //   warps 2-5 : softmax, one thread per query row
 #include "kernels.h"
+#include "launch.cuh"
 #include "ptx.cuh"
 
 namespace gam {
@@ -317,11 +318,10 @@ int launch_attention_relpos(const CUtensorMap* tmap_qkv, const CUtensorMap* tmap
                             int H, int dk, int d_model, cudaStream_t s) {
   const int nkb = (T + 127) / 128;
   if (nkb > kMaxKB || T > kRelPosMaxT || dk % 16 != 0 || dk > 64) return -1;
-  static int attr_set = 0;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(attention_relpos_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess) return -2;
-    attr_set = 1;
-  }
+  static PerDeviceOnce attr_once;
+  if (attr_once.first() &&
+      cudaFuncSetAttribute(attention_relpos_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess)
+    return -2;
   RelParams p;
   p.T = T;
   p.klen = klen;

@@ -930,10 +930,9 @@ static int launch_attention_long(const CUtensorMap* tmap_qkv, const int* klen, _
   p.ld_out = d_model;
   p.dk = dk;
   p.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(dk));
-  static int attr_set = 0;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     cudaFuncSetAttribute(attention_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    attr_set = 1;
   }
   const int smem = (2 * p.nkb + 2) * kTileBytes + 256 + 1024;
   attention_long_kernel<<<B * H, kLongThreads, smem, s>>>(*tmap_qkv, p);
@@ -952,10 +951,9 @@ static int launch_attention_persistent(const CUtensorMap* tmap_qkv, const int* k
   p.ld_out = d_model;
   p.dk = dk;
   p.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(dk));
-  static int attr_set = 0;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     cudaFuncSetAttribute(attention_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    attr_set = 1;
   }
   const int items = B * H;
   const int grid = items < num_sms ? items : num_sms;
@@ -976,10 +974,9 @@ static int launch_attention_resident(const CUtensorMap* tmap_qkv, const int* kle
   p.ld_out = d_model;
   p.dk = dk;
   p.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(dk));
-  static int attr_set = 0;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     cudaFuncSetAttribute(attention_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    attr_set = 1;
   }
   const int nqt = (T + 127) / 128;
   dim3 grid((nqt + p.QT - 1) / p.QT, H, B);
@@ -1017,10 +1014,9 @@ int launch_attention(const CUtensorMap* tmap_qkv, const int* klen, __half* out, 
   p.dk = dk;
   p.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(dk));
   const int smem = attention_smem_bytes(nkb);
-  static int attr_set = 0;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attention_smem_bytes(kMaxKB));
-    attr_set = 1;
   }
   dim3 grid((T + 127) / 128, H, B);
   attention_kernel<<<grid, kAttnThreads, smem, s>>>(*tmap_qkv, p);

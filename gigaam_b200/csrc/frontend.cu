@@ -7,6 +7,7 @@
 //       channels-last [B, T1, F1, C] fp16 so that stage 2 can fetch its im2col operand with strided
 //       TMA boxes (gigaam/encoder.py:59-70,111-123).
 #include "kernels.h"
+#include "launch.cuh"
 
 namespace gam {
 namespace {
@@ -336,11 +337,8 @@ int launch_logmel(const float* wav, int B, int n_samples, int n_frames, const fl
                   cudaStream_t s) {
   if (n_fft / 2 + 1 > kBinsPad || n_mels > 64 || (n_fft & 1)) return -1;
   const int smem = logmel_smem_bytes(n_fft);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_set = true;
-  }
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) cudaFuncSetAttribute(logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   dim3 grid((n_frames + kFr - 1) / kFr, B);
   logmel_kernel<<<grid, 256, smem, s>>>(wav, n_samples, n_frames, window, tcos, tsin, fb, mel, n_fft, hop, center, n_mels);
   return 0;

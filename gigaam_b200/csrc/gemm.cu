@@ -148,11 +148,9 @@ int launch_gemm_power(const CUtensorMap* ta, const CUtensorMap* tw, int M, int N
   p.out = out;
   p.ldo = ldo;
   p.scale = 1.0f / (2048.0f * 2048.0f * 8.0f * 8.0f);   // frames x 2^11, basis x 2^3 (engine.py DFT_*_SCALE), squared
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first())
     cudaFuncSetAttribute(gemm2_f16_tn_kernel<EPI_POWER_F32, A_2D>, cudaFuncAttributeMaxDynamicSharedMemorySize, kG2Smem);
-    attr = true;
-  }
   return launch_v2<EPI_POWER_F32, A_2D>(ta, tw, p, num_sms, s);
 }
 
@@ -176,11 +174,10 @@ int launch_gemm_conv1d(const CUtensorMap* ta3, const CUtensorMap* tw, int B, int
   p.out = out;
   p.ldo = ldo;
   p.scale = 1.f;
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     cudaFuncSetAttribute(gemm2_f16_tn_kernel<EPI_CONV_RELU_MASK_F16, A_CONV1D>, cudaFuncAttributeMaxDynamicSharedMemorySize, kG2Smem);
     cudaFuncSetAttribute(gemm2_f16_tn_kernel<EPI_CONV_RELU_MASK_F32, A_CONV1D>, cudaFuncAttributeMaxDynamicSharedMemorySize, kG2Smem);
-    attr = true;
   }
   return f32_out ? launch_v2<EPI_CONV_RELU_MASK_F32, A_CONV1D>(ta3, tw, p, num_sms, s)
                  : launch_v2<EPI_CONV_RELU_MASK_F16, A_CONV1D>(ta3, tw, p, num_sms, s);

@@ -2,10 +2,24 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
+#include <cstdint>
 #include <cstdlib>
 #include <utility>
 
 namespace gam {
+
+// cudaFuncSetAttribute (dynamic shared memory opt-in, cluster sizes) is per DEVICE: a process that drives several GPUs
+// must repeat it on each.  `first()` is true exactly once per device for the call site that owns the object.
+struct PerDeviceOnce {
+  std::atomic<uint64_t> seen{0};
+  bool first() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const uint64_t bit = 1ull << (dev & 63);
+    return (seen.fetch_or(bit) & bit) == 0;
+  }
+};
 
 inline bool pdl_enabled() {
   static int v = -1;

@@ -568,7 +568,10 @@ struct LaunchState {
 
 template <int NH, bool GLOB>
 int launch_nh(RnntClParams& p, int B, int V1, int smem_cap, bool info, cudaStream_t s) {
-  static LaunchState st;
+  static LaunchState per_device[64];   // function attributes and cluster occupancy are per device
+  int dev_index = 0;
+  cudaGetDevice(&dev_index);
+  LaunchState& st = per_device[dev_index & 63];
   const int cls_per = (V1 + kCl - 1) / kCl;
   const int cls_pad = (cls_per + 3) & ~3;
   const int fixed = static_cast<int>(sizeof(Smem<NH>)) + cls_pad * 4;
