@@ -583,6 +583,7 @@ int gam_encode(gam_handle* h, const float* mel, const int64_t* mel_len, int32_t 
   cudaMemcpyAsync(enc_len, p->len2, B * sizeof(int), cudaMemcpyDeviceToDevice, s);
   GAM_CHECK_LAUNCH(h, "encode");
   return 0;
+#undef XWIN
 }
 
 int gam_ctc_greedy(gam_handle* h, const float* enc, const int32_t* enc_len, int32_t B, int32_t T, void* workspace,
