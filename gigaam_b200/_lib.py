@@ -29,7 +29,7 @@ LAYER_FIELDS = (
     "ln_ff2_g", "ln_ff2_b", "ff2_w1", "ff2_b1", "ff2_w2", "ff2_b2", "ln_out_g", "ln_out_b",
     "w_qkv_rel", "b_qkv_rel", "pos_proj")
 
-REL_POS_MAX_T = 640   # GAM_REL_POS_MAX_T in include/gigaam_b200.h
+REL_POS_MAX_T = 768   # GAM_REL_POS_MAX_T in include/gigaam_b200.h
 
 
 class GamLayerWeights(C.Structure):
@@ -50,7 +50,8 @@ class GamWeights(C.Structure):
 EXPORTS = ("gam_create", "gam_destroy", "gam_last_error", "gam_version", "gam_logmel_frames", "gam_encoded_frames",
            "gam_workspace_bytes", "gam_logmel", "gam_encode", "gam_ctc_greedy", "gam_rnnt_greedy", "gam_test_gemm",
            "gam_test_attention", "gam_launch_count", "gam_profile_begin", "gam_profile_end", "gam_profile_class_count",
-           "gam_profile_class_name", "gam_logmel_workspace_bytes", "gam_logmel_tc", "gam_test_attention_relpos")
+           "gam_profile_class_name", "gam_logmel_workspace_bytes", "gam_logmel_tc", "gam_test_attention_relpos",
+           "gam_decode_workspace_bytes", "gam_test_gemm_ln")
 
 
 def lib_path() -> Path:
@@ -84,6 +85,10 @@ def load() -> C.CDLL:
     lib.gam_encoded_frames.restype = i64
     lib.gam_workspace_bytes.argtypes = [H, i32, i64]
     lib.gam_workspace_bytes.restype = i64
+    lib.gam_decode_workspace_bytes.argtypes = [H, i32, i32]
+    lib.gam_decode_workspace_bytes.restype = i64
+    lib.gam_test_gemm_ln.argtypes = [H, i32] + [c_vp] * 11 + [i32, i32, i32, C.c_float, c_vp, i64, c_vp]
+    lib.gam_test_gemm_ln.restype = C.c_int
     lib.gam_logmel.argtypes = [H, c_vp, i32, i64, c_vp, c_vp]
     lib.gam_logmel.restype = C.c_int
     lib.gam_encode.argtypes = [H, c_vp, c_vp, i32, i64, c_vp, i64, c_vp, c_vp, i32, c_vp]

@@ -27,7 +27,7 @@ namespace gam {
 namespace {
 
 constexpr int kThreads = 192;
-constexpr int kMaxKB = 5;                // up to 640 keys
+constexpr int kMaxKB = 6;                // up to 768 keys
 constexpr int kTile = 128 * 128;         // bytes of a 128-row x 64-column fp16 tile
 constexpr int kStageBytes = 4 * kTile;   // K, V, 2 position tiles
 constexpr int kSkewPitch = 52;           // words per private row (48 used)

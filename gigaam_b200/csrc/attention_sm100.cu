@@ -1,4 +1,4 @@
-// tcgen05 attention for the Conformer block (head_dim 48, T' <= 640, key-padding mask by length).
+// tcgen05 attention for the Conformer block (head_dim 48, T' <= 768, key-padding mask by length).
 // Replaces F.scaled_dot_product_attention / flash_attn_varlen in
 // gigaam/encoder.py:258-277 (RotaryPositionMultiHeadAttention) on the q/k/v produced by the fused
 // LN+RoPE -> GEMM kernels.
@@ -6,15 +6,11 @@
 //   qkv : [B*T, 2304] fp16 = [q(768) | k(768) | v(768)], head h at columns h*48 .. h*48+47 of each part
 //   out : [B*T, 768]  fp16
 //
-// One CTA per (q tile of 128 rows, head, utterance):
-//   warp 0    : TMA - Q tile and all K / V blocks (128 keys x 64 columns, SWIZZLE_128B; the 16 columns
-//               past the 48 real ones belong to the next head and are never multiplied: the QK^T MMA
-//               runs K = 3 x 16, and the 16 extra output columns of P.V are dropped)
-//   warp 1    : tcgen05.mma issue.  S = Q K^T (128 x 128 x 48) into TMEM, O += P V (128 x 64 x 128)
-//               with P from shared memory (K-major) and V straight from its [key, d] layout (MN-major B).
-//   warps 2-5 : softmax, one thread per query row (tcgen05.ld 32x32b), two passes over the key blocks:
-//               pass 1 = row max, pass 2 = exp2 / row sum / P -> smem.  S is recomputed in pass 2
-//               (tensor time is negligible here) so O never needs rescaling.
+// Common to both kernels below: K / V blocks are 128 keys x 64 columns (SWIZZLE_128B; the 16 columns past the 48
+// real ones belong to the next head and are never multiplied: QK^T runs K = 3 x 16 and the 16 extra output columns
+// of P.V are dropped); S = Q K^T (128 x 128 x 48) lands in TMEM; the softmax warps (one thread per query row,
+// tcgen05.ld 32x32b) write P back over the consumed S columns as packed fp16 (tcgen05.st) and O += P V runs as a
+// TS-mode tcgen05.mma with V straight from its [key, d] layout (MN-major B).
 #include "kernels.h"
 #include "launch.cuh"
 #include "ptx.cuh"
@@ -22,21 +18,8 @@
 namespace gam {
 namespace {
 
-constexpr int kAttnThreads = 192;
-constexpr int kMaxKB = 5;           // up to 640 keys
+constexpr int kMaxKB = 6;              // up to 768 keys (30 s segments of the reference's VAD, gigaam/vad_utils.py:85)
 constexpr int kTileBytes = 128 * 128;  // 128 rows x 64 fp16
-constexpr uint32_t kTmemColsAttn = 256;
-constexpr uint32_t kOCol = 128;
-
-struct AttnParams {
-  int T;
-  int nkb;
-  const int* klen;  // may be null
-  __half* out;
-  int ld_out;
-  int dk;
-  float scale_log2;
-};
 
 __device__ __forceinline__ float ex2(float x) {
   float y;
@@ -44,387 +27,6 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
-__global__ void __launch_bounds__(kAttnThreads) attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
-                                                                const AttnParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sP = smem + kTileBytes;                 // 2 chunks of 64 keys
-  uint8_t* sK = sP + 2 * kTileBytes;               // nkb tiles
-  uint8_t* sV = sK + p.nkb * kTileBytes;           // nkb tiles
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + p.nkb * kTileBytes);
-  uint64_t* kv_full = bars;            // [kMaxKB]
-  uint64_t* s_full = bars + kMaxKB;
-  uint64_t* s_empty = s_full + 1;
-  uint64_t* p_full = s_full + 2;
-  uint64_t* p_empty = s_full + 3;
-  uint64_t* o_full = s_full + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 5);
-
-  const int warp_idx = threadIdx.x >> 5;
-  const int q0 = blockIdx.x * 128;
-  const int h = blockIdx.y;
-  const int b = blockIdx.z;
-  const int row0 = b * p.T;
-  const int nkb = p.nkb;
-
-  if (warp_idx == 0 && ptx::elect_one()) {
-    ptx::prefetch_tmap(&tmap_qkv);
-    for (int i = 0; i < kMaxKB; ++i) ptx::mbar_init(&kv_full[i], 1);
-    ptx::mbar_init(s_full, 1);
-    ptx::mbar_init(s_empty, 4);
-    ptx::mbar_init(p_full, 4);
-    ptx::mbar_init(p_empty, 1);
-    ptx::mbar_init(o_full, 1);
-    ptx::fence_mbar_init();
-  }
-  if (warp_idx == 1) ptx::tmem_alloc<kTmemColsAttn>(tmem_slot);
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const int dmodel = p.ld_out;  // 768
-
-  if (warp_idx == 0) {
-    if (ptx::elect_one()) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        ptx::mbar_arrive_expect_tx(&kv_full[kb], (kb == 0 ? 3 : 2) * kTileBytes);
-        if (kb == 0) ptx::tma_load_2d(sQ, &tmap_qkv, &kv_full[0], h * p.dk, row0 + q0);
-        ptx::tma_load_2d(sK + kb * kTileBytes, &tmap_qkv, &kv_full[kb], dmodel + h * p.dk, row0 + kb * 128);
-        ptx::tma_load_2d(sV + kb * kTileBytes, &tmap_qkv, &kv_full[kb], 2 * dmodel + h * p.dk, row0 + kb * 128);
-      }
-    }
-  } else if (warp_idx == 1) {
-    constexpr uint32_t kIdescS = ptx::make_idesc_f16(128, 128, 0, 0);
-    constexpr uint32_t kIdescPV = ptx::make_idesc_f16(128, 64, 0, 1);  // B (= V) is MN-major
-    const int ksteps_qk = p.dk / 16;
-    int it = 0;
-    for (int pass = 0; pass < 2; ++pass) {
-      for (int kb = 0; kb < nkb; ++kb, ++it) {
-        if (it > 0) ptx::mbar_wait(s_empty, (it - 1) & 1);
-        if (pass == 0) ptx::mbar_wait(&kv_full[kb], 0);
-        ptx::tc_fence_after();
-        if (ptx::elect_one()) {
-          const uint32_t qa = ptx::smem_u32(sQ);
-          const uint32_t ka = ptx::smem_u32(sK + kb * kTileBytes);
-          for (int k = 0; k < ksteps_qk; ++k) {
-            ptx::mma_f16_ss(tmem_base, ptx::make_smem_desc_sw128(qa + k * 32, 16, 1024),
-                            ptx::make_smem_desc_sw128(ka + k * 32, 16, 1024), kIdescS, k != 0 ? 1u : 0u);
-          }
-          ptx::mma_commit(s_full);
-        }
-        __syncwarp();
-        if (pass == 1) {
-          ptx::mbar_wait(p_full, kb & 1);
-          ptx::tc_fence_after();
-          if (ptx::elect_one()) {
-            const uint32_t pa = ptx::smem_u32(sP);
-            const uint32_t va = ptx::smem_u32(sV + kb * kTileBytes);
-#pragma unroll
-            for (int ks = 0; ks < 8; ++ks) {
-              const uint64_t da = ptx::make_smem_desc_sw128(pa + (ks >> 2) * kTileBytes + (ks & 3) * 32, 16, 1024);
-              const uint64_t db = ptx::make_smem_desc_sw128(va + ks * 2048, 1024, 1024);
-              ptx::mma_f16_ss(tmem_base + kOCol, da, db, kIdescPV, (kb | ks) != 0 ? 1u : 0u);
-            }
-            ptx::mma_commit(p_empty);
-            if (kb == nkb - 1) ptx::mma_commit(o_full);
-          }
-          __syncwarp();
-        }
-      }
-    }
-  } else {
-    const int quad = warp_idx & 3;
-    const int lane = threadIdx.x & 31;
-    const int r = quad * 32 + lane;
-    const uint32_t t_s = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
-    int klen = p.T;
-    if (p.klen != nullptr) klen = min(max(p.klen[b], 0), p.T);
-    int it = 0;
-    float m = -INFINITY;
-    // ---------------- pass 1: row max over valid keys
-    for (int kb = 0; kb < nkb; ++kb, ++it) {
-      ptx::mbar_wait(s_full, it & 1);
-      ptx::tc_fence_after();
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        const int key0 = kb * 128 + c * 32;
-        if (key0 >= klen) break;
-        uint32_t v[32];
-        ptx::tmem_ld_32x32b_x32(t_s + c * 32, v);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (key0 + j < klen) m = fmaxf(m, __uint_as_float(v[j]));
-      }
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(s_empty);
-    }
-    if (m == -INFINITY) m = 0.f;
-    const float mc = m * p.scale_log2;
-    float sum = 0.f;
-    // ---------------- pass 2: p = exp2((s - m) * scale), P -> smem (K-major, SWIZZLE_128B)
-    for (int kb = 0; kb < nkb; ++kb, ++it) {
-      ptx::mbar_wait(s_full, it & 1);
-      ptx::tc_fence_after();
-      uint32_t pk[64];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int key0 = kb * 128 + c * 32;
-        uint32_t v[32];
-        ptx::tmem_ld_32x32b_x32(t_s + c * 32, v);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          float p0 = (key0 + j < klen) ? ex2(fmaf(__uint_as_float(v[j]), p.scale_log2, -mc)) : 0.f;
-          float p1 = (key0 + j + 1 < klen) ? ex2(fmaf(__uint_as_float(v[j + 1]), p.scale_log2, -mc)) : 0.f;
-          sum += p0 + p1;
-          __half2 hh = __floats2half2_rn(p0, p1);
-          pk[c * 16 + (j >> 1)] = *reinterpret_cast<uint32_t*>(&hh);
-        }
-      }
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(s_empty);
-      ptx::mbar_wait(p_empty, (kb & 1) ^ 1);
-#pragma unroll
-      for (int ch = 0; ch < 2; ++ch) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          uint4 val = make_uint4(pk[ch * 32 + j * 4], pk[ch * 32 + j * 4 + 1], pk[ch * 32 + j * 4 + 2], pk[ch * 32 + j * 4 + 3]);
-          *reinterpret_cast<uint4*>(sP + ch * kTileBytes + r * 128 + ((j ^ (r & 7)) << 4)) = val;
-        }
-      }
-      ptx::fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(p_full);
-    }
-    // ---------------- epilogue: O / sum -> fp16
-    ptx::mbar_wait(o_full, 0);
-    ptx::tc_fence_after();
-    const float inv = sum > 0.f ? 1.0f / sum : 0.f;
-    const int q = q0 + r;
-    __half* dst = p.out + static_cast<size_t>(row0 + q) * p.ld_out + h * p.dk;
-    for (int c = 0; c < p.dk; c += 16) {
-      uint32_t v[16];
-      ptx::tmem_ld_32x32b_x16(t_s + kOCol + c, v);
-      ptx::tmem_ld_wait();
-      if (q < p.T) {
-        uint32_t o[8];
-#pragma unroll
-        for (int j = 0; j < 16; j += 2) {
-          __half2 hh = __floats2half2_rn(__uint_as_float(v[j]) * inv, __uint_as_float(v[j + 1]) * inv);
-          o[j >> 1] = *reinterpret_cast<uint32_t*>(&hh);
-        }
-        uint4* d4 = reinterpret_cast<uint4*>(dst + c);
-        d4[0] = make_uint4(o[0], o[1], o[2], o[3]);
-        d4[1] = make_uint4(o[4], o[5], o[6], o[7]);
-      }
-    }
-    ptx::tc_fence_before();
-  }
-
-  __syncthreads();
-  if (warp_idx == 1) {
-    ptx::tc_fence_after();
-    ptx::tmem_dealloc<kTmemColsAttn>(tmem_base);
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// Resident-S variant for T <= 384 (every BASELINE config except the 25 s one): the whole score row of a
-// query lives in TMEM (nkb * 128 fp32 columns), so there is ONE softmax sweep per row (max, then exp) with
-// no recompute and no running-max correction, and only three hand-offs per query tile (S ready -> P ready
-// -> O ready).  When T <= 256 one CTA serves BOTH query tiles of a (utterance, head): K and V are fetched
-// once, two softmax warpgroups run side by side, and O aliases the first 64 columns of its tile's dead S
-// region so 2 x 256 TMEM columns suffice.
-constexpr int kResMaxKB = 3;
-constexpr int kResMaxQT = 2;
-
-struct AttnResParams {
-  int T, nkb, QT;
-  const int* klen;
-  __half* out;
-  int ld_out, dk;
-  float scale_log2;
-};
-
-__global__ void __launch_bounds__(64 + kResMaxQT * 128) attention_resident_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
-                                                                                    const AttnResParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int nkb = p.nkb, QT = p.QT;
-  uint8_t* sQ = smem;                                  // [QT] tiles
-  uint8_t* sK = sQ + QT * kTileBytes;                  // [nkb]
-  uint8_t* sV = sK + nkb * kTileBytes;                 // [nkb]
-  uint8_t* sP = sV + nkb * kTileBytes;                 // [QT][2 * nkb] chunks of 64 keys
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + QT * 2 * nkb * kTileBytes);
-  uint64_t* kv_full = bars;                            // [kResMaxKB]
-  uint64_t* s_full = kv_full + kResMaxKB;              // [kResMaxQT]
-  uint64_t* p_full = s_full + kResMaxQT;               // [kResMaxQT]
-  uint64_t* o_full = p_full + kResMaxQT;               // [kResMaxQT]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + kResMaxQT);
-
-  const int warp_idx = threadIdx.x >> 5;
-  const int h = blockIdx.y, b = blockIdx.z;
-  const int row0 = b * p.T;
-  const int q_base = blockIdx.x * QT * 128;
-  const int dmodel = p.ld_out;
-
-  if (warp_idx == 0 && ptx::elect_one()) {
-    ptx::prefetch_tmap(&tmap_qkv);
-    for (int i = 0; i < kResMaxKB; ++i) ptx::mbar_init(&kv_full[i], 1);
-    for (int i = 0; i < kResMaxQT; ++i) {
-      ptx::mbar_init(&s_full[i], 1);
-      ptx::mbar_init(&p_full[i], 4);
-      ptx::mbar_init(&o_full[i], 1);
-    }
-    ptx::fence_mbar_init();
-  }
-  if (warp_idx == 1) ptx::tmem_alloc<512>(tmem_slot);
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t s_cols = nkb * 128;
-
-  if (warp_idx == 0) {
-    if (ptx::elect_one()) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        ptx::mbar_arrive_expect_tx(&kv_full[kb], (2 + (kb == 0 ? QT : 0)) * kTileBytes);
-        if (kb == 0)
-          for (int qt = 0; qt < QT; ++qt)
-            ptx::tma_load_2d(sQ + qt * kTileBytes, &tmap_qkv, &kv_full[0], h * p.dk, row0 + q_base + qt * 128);
-        ptx::tma_load_2d(sK + kb * kTileBytes, &tmap_qkv, &kv_full[kb], dmodel + h * p.dk, row0 + kb * 128);
-        ptx::tma_load_2d(sV + kb * kTileBytes, &tmap_qkv, &kv_full[kb], 2 * dmodel + h * p.dk, row0 + kb * 128);
-      }
-    }
-  } else if (warp_idx == 1) {
-    constexpr uint32_t kIdescS = ptx::make_idesc_f16(128, 128, 0, 0);
-    constexpr uint32_t kIdescPV = ptx::make_idesc_f16(128, 64, 0, 1);
-    const int ksteps_qk = p.dk / 16;
-    // S[qt][:, kb*128 : kb*128+128] = Q[qt] K[kb]^T
-    for (int kb = 0; kb < nkb; ++kb) {
-      ptx::mbar_wait(&kv_full[kb], 0);
-      ptx::tc_fence_after();
-      if (ptx::elect_one()) {
-        const uint32_t ka = ptx::smem_u32(sK + kb * kTileBytes);
-        for (int qt = 0; qt < QT; ++qt) {
-          const uint32_t qa = ptx::smem_u32(sQ + qt * kTileBytes);
-          for (int k = 0; k < ksteps_qk; ++k)
-            ptx::mma_f16_ss(tmem_base + qt * s_cols + kb * 128, ptx::make_smem_desc_sw128(qa + k * 32, 16, 1024),
-                            ptx::make_smem_desc_sw128(ka + k * 32, 16, 1024), kIdescS, k != 0 ? 1u : 0u);
-          if (kb == nkb - 1) ptx::mma_commit(&s_full[qt]);
-        }
-      }
-      __syncwarp();
-    }
-    // O[qt] = P[qt] V   (O overwrites the first 64 columns of the tile's S region, dead once P is in smem)
-    for (int qt = 0; qt < QT; ++qt) {
-      ptx::mbar_wait(&p_full[qt], 0);
-      ptx::tc_fence_after();
-      if (ptx::elect_one()) {
-        const uint32_t pa = ptx::smem_u32(sP + qt * 2 * nkb * kTileBytes);
-        for (int kb = 0; kb < nkb; ++kb) {
-          const uint32_t va = ptx::smem_u32(sV + kb * kTileBytes);
-#pragma unroll
-          for (int ks = 0; ks < 8; ++ks) {
-            const uint64_t da = ptx::make_smem_desc_sw128(pa + (kb * 2 + (ks >> 2)) * kTileBytes + (ks & 3) * 32, 16, 1024);
-            const uint64_t db = ptx::make_smem_desc_sw128(va + ks * 2048, 1024, 1024);
-            ptx::mma_f16_ss(tmem_base + qt * s_cols, da, db, kIdescPV, (kb | ks) != 0 ? 1u : 0u);
-          }
-        }
-        ptx::mma_commit(&o_full[qt]);
-      }
-      __syncwarp();
-    }
-  } else if (warp_idx < 2 + 4 * QT) {
-    const int qt = (warp_idx - 2) >> 2;
-    const int quad = warp_idx & 3;
-    const int lane = threadIdx.x & 31;
-    const int r = quad * 32 + lane;
-    const uint32_t t_s = tmem_base + qt * s_cols + (static_cast<uint32_t>(quad * 32) << 16);
-    int klen = p.T;
-    if (p.klen != nullptr) klen = min(max(p.klen[b], 0), p.T);
-    const int nchunks = (klen + 31) >> 5;   // 32-key chunks holding at least one valid key
-    ptx::mbar_wait(&s_full[qt], 0);
-    ptx::tc_fence_after();
-    float m = -INFINITY;
-#pragma unroll 1
-    for (int c = 0; c < nchunks; ++c) {
-      uint32_t v[32];
-      ptx::tmem_ld_32x32b_x32(t_s + c * 32, v);
-      ptx::tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (c * 32 + j < klen) m = fmaxf(m, __uint_as_float(v[j]));
-    }
-    if (m == -INFINITY) m = 0.f;
-    const float mc = m * p.scale_log2;
-    float sum = 0.f;
-    uint8_t* myP = sP + qt * 2 * nkb * kTileBytes;
-#pragma unroll 1
-    for (int c = 0; c < nkb * 4; ++c) {
-      uint32_t pk[16];
-      if (c < nchunks) {
-        uint32_t v[32];
-        ptx::tmem_ld_32x32b_x32(t_s + c * 32, v);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          const float p0 = (c * 32 + j < klen) ? ex2(fmaf(__uint_as_float(v[j]), p.scale_log2, -mc)) : 0.f;
-          const float p1 = (c * 32 + j + 1 < klen) ? ex2(fmaf(__uint_as_float(v[j + 1]), p.scale_log2, -mc)) : 0.f;
-          sum += p0 + p1;
-          __half2 hh = __floats2half2_rn(p0, p1);
-          pk[j >> 1] = *reinterpret_cast<uint32_t*>(&hh);
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) pk[j] = 0u;
-      }
-      // 32 keys = 64 bytes = pieces (c & 1) * 4 .. +3 of row r in 64-key chunk c >> 1 (K-major, SWIZZLE_128B)
-      uint8_t* chunk = myP + (c >> 1) * kTileBytes + r * 128;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int piece = (c & 1) * 4 + j;
-        *reinterpret_cast<uint4*>(chunk + ((piece ^ (r & 7)) << 4)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-      }
-    }
-    ptx::tc_fence_before();
-    ptx::fence_proxy_async_smem();
-    __syncwarp();
-    if (lane == 0) ptx::mbar_arrive(&p_full[qt]);
-    ptx::mbar_wait(&o_full[qt], 0);
-    ptx::tc_fence_after();
-    const float inv = sum > 0.f ? 1.0f / sum : 0.f;
-    const int q = q_base + qt * 128 + r;
-    __half* dst = p.out + static_cast<size_t>(row0 + q) * p.ld_out + h * p.dk;
-    for (int c = 0; c < p.dk; c += 16) {
-      uint32_t v[16];
-      ptx::tmem_ld_32x32b_x16(t_s + c, v);
-      ptx::tmem_ld_wait();
-      if (q < p.T) {
-        uint32_t o[8];
-#pragma unroll
-        for (int j = 0; j < 16; j += 2) {
-          __half2 hh = __floats2half2_rn(__uint_as_float(v[j]) * inv, __uint_as_float(v[j + 1]) * inv);
-          o[j >> 1] = *reinterpret_cast<uint32_t*>(&hh);
-        }
-        uint4* d4 = reinterpret_cast<uint4*>(dst + c);
-        d4[0] = make_uint4(o[0], o[1], o[2], o[3]);
-        d4[1] = make_uint4(o[4], o[5], o[6], o[7]);
-      }
-    }
-    ptx::tc_fence_before();
-  }
-
-  __syncthreads();
-  if (warp_idx == 1) {
-    ptx::tc_fence_after();
-    ptx::tmem_dealloc<512>(tmem_base);
-  }
-}
 
 // ---------------------------------------------------------------------------------------------------------
 // Persistent variant for T <= 256 (the headline config, T' = 251): one CTA per SM loops over (utterance, head)
@@ -444,7 +46,6 @@ __global__ void __launch_bounds__(128 + 256, 1) attention_persistent_kernel(cons
                                                                           const AttnPersParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  ptx::pdl_launch_dependents();
   const int nkb = p.nkb;                    // 1 or 2: key blocks == query tiles
   const int item_bytes = 3 * nkb * kTileBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * item_bytes);
@@ -477,7 +78,6 @@ __global__ void __launch_bounds__(128 + 256, 1) attention_persistent_kernel(cons
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  ptx::pdl_wait();   // PDL: the set-up above overlapped the QKV GEMM's tail
 
   if (warp_idx == 0) {
     // ===================================================== TMA producer
@@ -691,7 +291,7 @@ __global__ void __launch_bounds__(128 + 256, 1) attention_persistent_kernel(cons
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Long-sequence variant (any T <= 640, used for T > 256): one CTA per (utterance, head) keeps ALL K / V blocks of
+// Long-sequence variant (any T <= 768, used for T > 256): one CTA per (utterance, head) keeps ALL K / V blocks of
 // the head resident in shared memory and walks the query tiles; two softmax warpgroups (each with its own MMA
 // issuer warp, S slot, P alias and O accumulator in TMEM) process alternate query tiles concurrently.  A score
 // row no longer fits TMEM, so each query tile makes two sweeps over the key blocks (max, then exp / P.V) with
@@ -917,8 +517,6 @@ __global__ void __launch_bounds__(kLongThreads, 1) attention_long_kernel(const _
 
 }  // namespace
 
-int attention_smem_bytes(int nkb) { return (3 + 2 * nkb) * kTileBytes + 128 + 1024; }
-
 static int launch_attention_long(const CUtensorMap* tmap_qkv, const int* klen, __half* out, int B, int T, int H, int dk,
                                  int d_model, cudaStream_t s) {
   AttnLongParams p;
@@ -958,69 +556,14 @@ static int launch_attention_persistent(const CUtensorMap* tmap_qkv, const int* k
   const int items = B * H;
   const int grid = items < num_sms ? items : num_sms;
   const int smem = 2 * 3 * p.nkb * kTileBytes + 256 + 1024;
-  return launch_pdl(attention_persistent_kernel, dim3(grid), dim3(128 + 128 * p.nkb), smem, s, *tmap_qkv, p) == cudaSuccess ? 0 : -2;
+  return launch_k(attention_persistent_kernel, dim3(grid), dim3(128 + 128 * p.nkb), smem, s, *tmap_qkv, p) == cudaSuccess ? 0 : -2;
 }
-static int attention_res_smem_bytes(int nkb, int QT) { return (QT + 2 * nkb + QT * 2 * nkb) * kTileBytes + 128 + 1024; }
-
-static int launch_attention_resident(const CUtensorMap* tmap_qkv, const int* klen, __half* out, int B, int T, int H, int dk,
-                                     int d_model, cudaStream_t s) {
-  const int nkb = (T + 127) / 128;
-  AttnResParams p;
-  p.T = T;
-  p.nkb = nkb;
-  p.QT = nkb <= 2 ? 2 : 1;
-  p.klen = klen;
-  p.out = out;
-  p.ld_out = d_model;
-  p.dk = dk;
-  p.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(dk));
-  static PerDeviceOnce attr_once;
-  if (attr_once.first()) {
-    cudaFuncSetAttribute(attention_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  }
-  const int nqt = (T + 127) / 128;
-  dim3 grid((nqt + p.QT - 1) / p.QT, H, B);
-  attention_resident_kernel<<<grid, 64 + p.QT * 128, attention_res_smem_bytes(nkb, p.QT), s>>>(*tmap_qkv, p);
-  return 0;
-}
-
 int launch_attention(const CUtensorMap* tmap_qkv, const int* klen, __half* out, int B, int T, int H, int dk, int d_model,
-                     cudaStream_t s) {
+                     int num_sms, cudaStream_t s) {
   const int nkb = (T + 127) / 128;
   if (nkb > kMaxKB || dk % 16 != 0 || dk > 64) return -1;
-  static int force_v1 = -1;
-  if (force_v1 < 0) {
-    const char* e = getenv("GAM_ATTN_V1");
-    force_v1 = (e && e[0] == '1') ? 1 : 0;
-  }
-  static int force_v2 = -1, num_sms = 0;
-  if (force_v2 < 0) {
-    const char* e = getenv("GAM_ATTN_V2");
-    force_v2 = (e && e[0] == '1') ? 1 : 0;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-  }
-  if (nkb <= 2 && !force_v1 && !force_v2)
-    return launch_attention_persistent(tmap_qkv, klen, out, B, T, H, dk, d_model, num_sms, s);
-  if (!force_v1 && !force_v2) return launch_attention_long(tmap_qkv, klen, out, B, T, H, dk, d_model, s);
-  if (nkb <= kResMaxKB && !force_v1) return launch_attention_resident(tmap_qkv, klen, out, B, T, H, dk, d_model, s);
-  AttnParams p;
-  p.T = T;
-  p.nkb = nkb;
-  p.klen = klen;
-  p.out = out;
-  p.ld_out = d_model;
-  p.dk = dk;
-  p.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(dk));
-  const int smem = attention_smem_bytes(nkb);
-  static PerDeviceOnce attr_once;
-  if (attr_once.first()) {
-    cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attention_smem_bytes(kMaxKB));
-  }
-  dim3 grid((T + 127) / 128, H, B);
-  attention_kernel<<<grid, kAttnThreads, smem, s>>>(*tmap_qkv, p);
-  return 0;
+  if (nkb <= 2) return launch_attention_persistent(tmap_qkv, klen, out, B, T, H, dk, d_model, num_sms, s);
+  return launch_attention_long(tmap_qkv, klen, out, B, T, H, dk, d_model, s);
 }
 
 }  // namespace gam

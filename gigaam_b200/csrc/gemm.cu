@@ -1,5 +1,4 @@
-// Instantiations and host launchers of the tcgen05 GEMMs (gemm_sm100.cuh: one CTA per 128 x 256 tile;
-// gemm2_sm100.cuh: CTA pairs, 256 x 256 tiles, cta_group::2 -- the default).
+// Instantiations and host launchers of the CTA-pair tcgen05 GEMM (gemm2_sm100.cuh: 256 x 256 tiles, cta_group::2).
 #include <cstdlib>
 
 #include "gemm2_sm100.cuh"
@@ -11,25 +10,6 @@ namespace {
 
 constexpr int kBN = 256;
 
-bool use_v1() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = std::getenv("GAM_GEMM_V1");
-    v = (e && e[0] == '1') ? 1 : 0;
-  }
-  return v == 1;
-}
-
-template <int EPI, int AMODE>
-int launch_v1(const CUtensorMap* ta, const CUtensorMap* tw, const GemmParams& p, int num_sms, cudaStream_t s) {
-  auto kern = gemm_f16_tn_kernel<kBN, EPI, AMODE>;
-  const int tiles = p.num_m_tiles * p.num_n_tiles;
-  const int grid = tiles < num_sms ? tiles : num_sms;
-  if (grid <= 0) return 0;
-  kern<<<grid, kGemmThreads, GemmSmem<kBN>::kTotal, s>>>(*ta, *tw, p);
-  return cudaPeekAtLastError() == cudaSuccess ? 0 : -2;
-}
-
 // p.num_m_tiles counts 128-row blocks on entry; the pair kernel wants 256-row pair tiles
 template <int EPI, int AMODE>
 int launch_v2(const CUtensorMap* ta, const CUtensorMap* tw, GemmParams p, int num_sms, cudaStream_t s,
@@ -40,21 +20,12 @@ int launch_v2(const CUtensorMap* ta, const CUtensorMap* tw, GemmParams p, int nu
   const int max_pairs = num_sms / 2;
   const int npairs = tiles < max_pairs ? tiles : max_pairs;
   if (npairs <= 0) return 0;
-  return launch_pdl(kern, dim3(2 * npairs), dim3(kG2Threads), kG2Smem, s, *ta, ta2 ? *ta2 : *ta, *tw, p) == cudaSuccess ? 0 : -2;
-}
-
-template <int EPI, int AMODE>
-int launch_one(const CUtensorMap* ta, const CUtensorMap* tw, const GemmParams& p, int num_sms, cudaStream_t s) {
-  return use_v1() ? launch_v1<EPI, AMODE>(ta, tw, p, num_sms, s) : launch_v2<EPI, AMODE>(ta, tw, p, num_sms, s);
+  return launch_k(kern, dim3(2 * npairs), dim3(kG2Threads), kG2Smem, s, *ta, ta2 ? *ta2 : *ta, *tw, p) == cudaSuccess ? 0 : -2;
 }
 
 template <int EPI, int AMODE>
 int set_attr() {
-  auto k1 = gemm_f16_tn_kernel<kBN, EPI, AMODE>;
-  auto k2 = gemm2_f16_tn_kernel<EPI, AMODE>;
-  int rc = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<kBN>::kTotal) == cudaSuccess ? 0 : -1;
-  rc |= cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, kG2Smem) == cudaSuccess ? 0 : -1;
-  return rc;
+  return cudaFuncSetAttribute(gemm2_f16_tn_kernel<EPI, AMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kG2Smem) == cudaSuccess ? 0 : -1;
 }
 
 }  // namespace
@@ -66,7 +37,11 @@ int gemm_init() {
   rc |= set_attr<EPI_BIAS_GLU_F16, A_2D>();
   rc |= set_attr<EPI_BIAS_RES_F32, A_2D>();
   rc |= set_attr<EPI_BIAS_F32, A_2D>();
+  rc |= set_attr<EPI_BIAS_RES_LN_F32, A_2D>();
   rc |= set_attr<EPI_CONV_RELU_MASK_F16, A_CONV>();
+  rc |= set_attr<EPI_POWER_F32, A_2D>();
+  rc |= set_attr<EPI_CONV_RELU_MASK_F16, A_CONV1D>();
+  rc |= set_attr<EPI_CONV_RELU_MASK_F32, A_CONV1D>();
   return rc;
 }
 
@@ -85,20 +60,41 @@ int launch_gemm(int kind, const CUtensorMap* ta, const CUtensorMap* tw, int M, i
   p.ldo = ldo;
   p.scale = scale;
   switch (kind) {
-    case GEMM_BIAS_F16: return launch_one<EPI_BIAS_F16, A_2D>(ta, tw, p, num_sms, s);
-    case GEMM_BIAS_SILU_F16: return launch_one<EPI_BIAS_SILU_F16, A_2D>(ta, tw, p, num_sms, s);
-    case GEMM_BIAS_GLU_F16: return launch_one<EPI_BIAS_GLU_F16, A_2D>(ta, tw, p, num_sms, s);
-    case GEMM_BIAS_RES_F32: return launch_one<EPI_BIAS_RES_F32, A_2D>(ta, tw, p, num_sms, s);
-    case GEMM_BIAS_F32: return launch_one<EPI_BIAS_F32, A_2D>(ta, tw, p, num_sms, s);
+    case GEMM_BIAS_F16: return launch_v2<EPI_BIAS_F16, A_2D>(ta, tw, p, num_sms, s);
+    case GEMM_BIAS_SILU_F16: return launch_v2<EPI_BIAS_SILU_F16, A_2D>(ta, tw, p, num_sms, s);
+    case GEMM_BIAS_GLU_F16: return launch_v2<EPI_BIAS_GLU_F16, A_2D>(ta, tw, p, num_sms, s);
+    case GEMM_BIAS_RES_F32: return launch_v2<EPI_BIAS_RES_F32, A_2D>(ta, tw, p, num_sms, s);
+    case GEMM_BIAS_F32: return launch_v2<EPI_BIAS_F32, A_2D>(ta, tw, p, num_sms, s);
     default: return -1;
   }
+}
+
+// x = res + scale * (A W^T + bias) (fp32, N = 768) followed by the LayerNorm(s) described by `ln` (gemm_params.cuh: LnFuse)
+// in the same launch.  The cross-CTA statistics exchange needs the three n-tiles of a 256-row block to run on different,
+// co-resident CTA pairs: at least 3 pairs, grid <= #SMs (always true here).
+int launch_gemm_res_ln(const CUtensorMap* ta, const CUtensorMap* tw, int M, int K, const float* bias, const float* res, float* out,
+                       float scale, const LnFuse& ln, int num_sms, cudaStream_t s) {
+  if (K % kGemmBK != 0 || M <= 0 || num_sms < 6 || ln.mode < 1 || ln.mode > 3) return -1;
+  GemmParams p{};
+  p.M = M;
+  p.N = kLnD;
+  p.num_m_tiles = (M + kGemmBM - 1) / kGemmBM;
+  p.num_n_tiles = kLnD / kBN;
+  p.num_k_blocks = K / kGemmBK;
+  p.bias = bias;
+  p.res = res;
+  p.out = out;
+  p.ldo = kLnD;
+  p.scale = scale;
+  p.ln = ln;
+  return launch_v2<EPI_BIAS_RES_LN_F32, A_2D>(ta, tw, p, num_sms, s);
 }
 
 // D[:, :n1] = A1 W[:n1]^T + b, D[:, n1:] = A2 W[n1:]^T + b  (fp16 out) in ONE launch of the pair kernel: more tiles per
 // launch = less wave quantisation (QK + V: 378 + 189 tiles on 74 pairs = 6 + 3 waves apart, 8 together) and one launch less.
 int launch_gemm_dual_a(const CUtensorMap* ta1, const CUtensorMap* ta2, int n1, const CUtensorMap* tw, int M, int N, int K,
                        const float* bias, void* out, int ldo, int num_sms, cudaStream_t s) {
-  if (N % kBN != 0 || n1 % kBN != 0 || n1 <= 0 || n1 >= N || K % kGemmBK != 0 || M <= 0 || use_v1()) return -1;
+  if (N % kBN != 0 || n1 % kBN != 0 || n1 <= 0 || n1 >= N || K % kGemmBK != 0 || M <= 0) return -1;
   GemmParams p{};
   p.M = M;
   p.N = N;
@@ -132,7 +128,7 @@ int launch_gemm_conv(const CUtensorMap* ta4, const CUtensorMap* tw, int B, int T
   p.out = out;
   p.ldo = ldo;
   p.scale = 1.f;
-  return launch_one<EPI_CONV_RELU_MASK_F16, A_CONV>(ta4, tw, p, num_sms, s);
+  return launch_v2<EPI_CONV_RELU_MASK_F16, A_CONV>(ta4, tw, p, num_sms, s);
 }
 
 // power spectrum of a split-precision DFT: D = A W^T with W tiles [128 cos | 128 sin]; out[:, N/2] = re^2 + im^2
@@ -148,9 +144,6 @@ int launch_gemm_power(const CUtensorMap* ta, const CUtensorMap* tw, int M, int N
   p.out = out;
   p.ldo = ldo;
   p.scale = 1.0f / (2048.0f * 2048.0f * 8.0f * 8.0f);   // frames x 2^11, basis x 2^3 (engine.py DFT_*_SCALE), squared
-  static PerDeviceOnce attr_once;
-  if (attr_once.first())
-    cudaFuncSetAttribute(gemm2_f16_tn_kernel<EPI_POWER_F32, A_2D>, cudaFuncAttributeMaxDynamicSharedMemorySize, kG2Smem);
   return launch_v2<EPI_POWER_F32, A_2D>(ta, tw, p, num_sms, s);
 }
 
@@ -174,11 +167,6 @@ int launch_gemm_conv1d(const CUtensorMap* ta3, const CUtensorMap* tw, int B, int
   p.out = out;
   p.ldo = ldo;
   p.scale = 1.f;
-  static PerDeviceOnce attr_once;
-  if (attr_once.first()) {
-    cudaFuncSetAttribute(gemm2_f16_tn_kernel<EPI_CONV_RELU_MASK_F16, A_CONV1D>, cudaFuncAttributeMaxDynamicSharedMemorySize, kG2Smem);
-    cudaFuncSetAttribute(gemm2_f16_tn_kernel<EPI_CONV_RELU_MASK_F32, A_CONV1D>, cudaFuncAttributeMaxDynamicSharedMemorySize, kG2Smem);
-  }
   return f32_out ? launch_v2<EPI_CONV_RELU_MASK_F32, A_CONV1D>(ta3, tw, p, num_sms, s)
                  : launch_v2<EPI_CONV_RELU_MASK_F16, A_CONV1D>(ta3, tw, p, num_sms, s);
 }

@@ -19,7 +19,7 @@
 // residual / activation are applied.  Residual reads are software-pipelined one chunk ahead; with eight warps
 // that keeps 16 chunk loads in flight per SM, enough to hide L2 latency behind the next tile's main loop.
 #pragma once
-#include "gemm_sm100.cuh"
+#include "gemm_params.cuh"
 
 namespace gam {
 
@@ -34,6 +34,174 @@ constexpr int kG2WarpBias = 128 * 4;          // per-warp copy of its 128 bias v
 constexpr int kG2EpiBytes = kG2EpiWarps * (kG2WarpStage + kG2WarpBias);
 constexpr int kG2BarBytes = 256;
 constexpr int kG2Smem = kG2Stages * kG2StageBytes + kG2EpiBytes + kG2BarBytes + 1024;
+
+// ------------------------------------------------------------------------------------------------------------------
+// LayerNorm tail of EPI_BIAS_RES_LN_F32 (LnFuse in gemm_params.cuh).  Called by one epilogue warp after it has stored
+// x = res + scale * (acc + bias) for its 32 rows x 128 columns; thread layout as in the store loop: lane covers rows
+// i * 4 + (lane >> 3), i = 0..7, and 4 consecutive columns (lane & 7) * 4 of every 32-column chunk.
+constexpr int kLnSlots = 6;          // 3 n-tiles x 2 column halves of a 768-wide row
+constexpr int kLnD = 768;
+
+__device__ __forceinline__ void ln_publish(float (&s1)[8], float (&s2)[8], float2* stats, unsigned int* cnt, long long warp_row0,
+                                           int rows_valid, int group, int slot, int lane) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+      s1[i] += __shfl_xor_sync(0xffffffffu, s1[i], o);
+      s2[i] += __shfl_xor_sync(0xffffffffu, s2[i], o);
+    }
+  }
+  float ps = 0.f, pq = 0.f;   // lane l publishes row (l & 7) * 4 + (l >> 3)
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if ((lane & 7) == i) { ps = s1[i]; pq = s2[i]; }
+  const int pr = (lane & 7) * 4 + (lane >> 3);
+  if (pr < rows_valid) stats[(warp_row0 + pr) * kLnSlots + slot] = make_float2(ps, pq);
+  __syncwarp();
+  if (lane == 0) {
+    __threadfence();              // this warp's x and stats stores (ordered before by the __syncwarp) become visible GPU-wide ...
+    atomicAdd(&cnt[group], 1u);   // ... before the arrival is counted
+  }
+}
+
+// wait until all six column slices of this warp's rows have been published.  A peer that never arrives (the grid was
+// not co-resident) traps after ~1-2 s instead of hanging the device
+__device__ __forceinline__ void ln_wait(const unsigned int* cnt, int group, int lane) {
+  if (lane == 0) {
+    unsigned int v = 0;
+    long long spins = 0;
+    while (true) {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(cnt + group) : "memory");
+      if (v >= static_cast<unsigned int>(kLnSlots)) break;
+      __nanosleep(64);
+      if (++spins > (1ll << 24)) __trap();
+    }
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ void ln_row_stats(const float2* stats, long long warp_row0, int rows_valid, int lane, float eps,
+                                             float (&mean)[8], float (&rstd)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = i * 4 + (lane >> 3);
+    float s = 0.f, q = 0.f;
+    if (r < rows_valid) {
+      const float2* sp = stats + (warp_row0 + r) * kLnSlots;
+#pragma unroll
+      for (int j = 0; j < kLnSlots; ++j) {   // fixed order: bit-reproducible
+        const float2 v = __ldcg(sp + j);
+        s += v.x;
+        q += v.y;
+      }
+    }
+    mean[i] = s * (1.0f / kLnD);
+    rstd[i] = rsqrtf(fmaxf(q * (1.0f / kLnD) - mean[i] * mean[i], 0.f) + eps);
+  }
+}
+
+__device__ __forceinline__ uint2 ln_pack4(float4 v) {
+  return make_uint2(pack_half2(v.x, v.y), pack_half2(v.z, v.w));
+}
+__device__ __forceinline__ float4 ln_affine(float4 v, float mean, float rstd, float4 g, float4 b) {
+  return make_float4((v.x - mean) * rstd * g.x + b.x, (v.y - mean) * rstd * g.y + b.y, (v.z - mean) * rstd * g.z + b.z,
+                     (v.w - mean) * rstd * g.w + b.w);
+}
+
+__device__ __noinline__ void ln_tail(const GemmParams& p, float (&s1)[8], float (&s2)[8], long long warp_row0, int rows_valid,
+                                     int group, int n_blk, int half, int lane) {
+  const LnFuse& f = p.ln;
+  const int slot = 2 * n_blk + half;
+  const int col0 = n_blk * 256 + half * 128 + (lane & 7) * 4;   // + 32 * chunk
+  ln_publish(s1, s2, f.stats, f.cnt, warp_row0, rows_valid, group, slot, lane);
+  if (rows_valid <= 0) {
+    if (f.mode == 3 && f.g2 != nullptr && lane == 0) atomicAdd(&f.cnt2[group], 1u);   // keeps the second round's count complete
+    return;
+  }
+  ln_wait(f.cnt, group, lane);
+  float mean[8], rstd[8];
+  ln_row_stats(f.stats, warp_row0, rows_valid, lane, f.eps, mean, rstd);
+  const float* xin = reinterpret_cast<const float*>(p.out);
+  if (f.mode == 1 || f.mode == 2) {
+#pragma unroll 1
+    for (int ci = 0; ci < 4; ++ci) {
+      const int col = col0 + ci * 32;
+      const float4 g = __ldg(reinterpret_cast<const float4*>(f.g + col));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(f.b + col));
+      // rotary partner: the float4 24 columns away inside the same 48-wide head (utils.py:83-100); it may belong to
+      // another CTA's tile -- visible, because all six slots of these rows have been published
+      const int q = col % 48;
+      const bool lo = q < 24;
+      const int colp = lo ? col + 24 : col - 24;
+      float4 gp = g, bp = b;
+      if (f.mode == 2) {
+        gp = __ldg(reinterpret_cast<const float4*>(f.g + colp));
+        bp = __ldg(reinterpret_cast<const float4*>(f.b + colp));
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = i * 4 + (lane >> 3);
+        if (r < rows_valid) {
+          const size_t row = static_cast<size_t>(warp_row0 + r);
+          const float4 u = ln_affine(__ldcg(reinterpret_cast<const float4*>(xin + row * p.ldo + col)), mean[i], rstd[i], g, b);
+          *reinterpret_cast<uint2*>(f.out16 + row * kLnD + col) = ln_pack4(u);
+          if (f.mode == 2) {
+            const float4 up = ln_affine(__ldcg(reinterpret_cast<const float4*>(xin + row * p.ldo + colp)), mean[i], rstd[i], gp, bp);
+            const int t = static_cast<int>(row % static_cast<size_t>(f.T));
+            const float4 c = __ldg(reinterpret_cast<const float4*>(f.rope_cos + static_cast<size_t>(t) * f.half_dim + (lo ? q : q - 24)));
+            const float4 s = __ldg(reinterpret_cast<const float4*>(f.rope_sin + static_cast<size_t>(t) * f.half_dim + (lo ? q : q - 24)));
+            const float sg = lo ? -1.f : 1.f;
+            *reinterpret_cast<uint2*>(f.rope16 + row * kLnD + col) =
+                ln_pack4(make_float4(fmaf(sg * up.x, s.x, u.x * c.x), fmaf(sg * up.y, s.y, u.y * c.y), fmaf(sg * up.z, s.z, u.z * c.z),
+                                     fmaf(sg * up.w, s.w, u.w * c.w)));
+          }
+        }
+      }
+    }
+    return;
+  }
+  // mode 3: xout = LN(x) in fp32 (norm_out, encoder.py:497), then -- unless this is the last layer -- the next layer's
+  // first LayerNorm of that result, with a second statistics round
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
+#pragma unroll 1
+  for (int ci = 0; ci < 4; ++ci) {
+    const int col = col0 + ci * 32;
+    const float4 g = __ldg(reinterpret_cast<const float4*>(f.g + col));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(f.b + col));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = i * 4 + (lane >> 3);
+      if (r < rows_valid) {
+        const size_t row = static_cast<size_t>(warp_row0 + r);
+        const float4 y = ln_affine(__ldcg(reinterpret_cast<const float4*>(xin + row * p.ldo + col)), mean[i], rstd[i], g, b);
+        *reinterpret_cast<float4*>(f.xout + row * kLnD + col) = y;
+        s1[i] += (y.x + y.y) + (y.z + y.w);
+        s2[i] = fmaf(y.x, y.x, fmaf(y.y, y.y, fmaf(y.z, y.z, fmaf(y.w, y.w, s2[i]))));
+      }
+    }
+  }
+  if (f.g2 == nullptr) return;
+  ln_publish(s1, s2, f.stats2, f.cnt2, warp_row0, rows_valid, group, slot, lane);
+  ln_wait(f.cnt2, group, lane);
+  ln_row_stats(f.stats2, warp_row0, rows_valid, lane, f.eps, mean, rstd);
+#pragma unroll 1
+  for (int ci = 0; ci < 4; ++ci) {
+    const int col = col0 + ci * 32;
+    const float4 g = __ldg(reinterpret_cast<const float4*>(f.g2 + col));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(f.b2 + col));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = i * 4 + (lane >> 3);
+      if (r < rows_valid) {
+        const size_t row = static_cast<size_t>(warp_row0 + r);
+        *reinterpret_cast<uint2*>(f.out16 + row * kLnD + col) =
+            ln_pack4(ln_affine(__ldcg(reinterpret_cast<const float4*>(f.xout + row * kLnD + col)), mean[i], rstd[i], g, b));
+      }
+    }
+  }
+}
 
 template <int EPI, int AMODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kG2Threads, 1)
@@ -55,7 +223,6 @@ gemm2_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   uint64_t* tmem_empty = tmem_full + 2;           // [2]  (leader's copy is the live one)
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
-  ptx::pdl_launch_dependents();
   const int warp_idx = threadIdx.x >> 5;
   const uint32_t rank = ptx::cluster_ctarank();
   const bool leader = rank == 0;
@@ -82,8 +249,6 @@ gemm2_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   ptx::cluster_sync();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
-  // everything above overlapped the previous kernel's tail (PDL); from here on we touch its outputs
-  ptx::pdl_wait();
 
   if (warp_idx == 0) {
     // ===================================================== TMA producer (both CTAs)
@@ -217,9 +382,16 @@ gemm2_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         row_live = blk_ok && (t0 + (lane >> 4)) < p.conv_len2[b];
       }
 
+      constexpr bool kRes = EPI == EPI_BIAS_RES_F32 || EPI == EPI_BIAS_RES_LN_F32;
+      constexpr bool kLn = EPI == EPI_BIAS_RES_LN_F32;
       [[maybe_unused]] float4 rr[2][8];
       [[maybe_unused]] const int c4 = (lane & 7) * 4;
-      if constexpr (EPI == EPI_BIAS_RES_F32) {
+      [[maybe_unused]] float ls1[8], ls2[8];   // LayerNorm partial sums of this thread's 8 rows (kLn)
+      if constexpr (kLn) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ls1[i] = ls2[i] = 0.f;
+      }
+      if constexpr (kRes) {
         // first chunk's residual goes out before we even wait for the accumulator
         const size_t col = static_cast<size_t>(n_blk) * BN + half * 128 + c4;
 #pragma unroll
@@ -235,13 +407,13 @@ gemm2_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       __syncwarp();
       const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(quad * 32) << 16);
 
-      if constexpr (EPI == EPI_BIAS_RES_F32 || EPI == EPI_BIAS_F32 || EPI == EPI_CONV_RELU_MASK_F32) {
+      if constexpr (kRes || EPI == EPI_BIAS_F32 || EPI == EPI_CONV_RELU_MASK_F32) {
         float* outp = reinterpret_cast<float*>(p.out);
 #pragma unroll
         for (int ci = 0; ci < 4; ++ci) {
           const int c = half * 128 + ci * 32;
           const size_t col = static_cast<size_t>(n_blk) * BN + c + c4;
-          if constexpr (EPI == EPI_BIAS_RES_F32) {
+          if constexpr (kRes) {
             if (ci + 1 < 4) {   // residual of the next chunk in flight while this one is transposed and stored
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
@@ -268,10 +440,14 @@ gemm2_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             if (r < rows_valid) {
               float4 a = *reinterpret_cast<const float4*>(stg + r * 36 + c4);
               a.x += bv.x; a.y += bv.y; a.z += bv.z; a.w += bv.w;
-              if constexpr (EPI == EPI_BIAS_RES_F32) {
+              if constexpr (kRes) {
                 const float4 x = rr[ci & 1][i];
                 a.x = fmaf(p.scale, a.x, x.x); a.y = fmaf(p.scale, a.y, x.y);
                 a.z = fmaf(p.scale, a.z, x.z); a.w = fmaf(p.scale, a.w, x.w);
+              }
+              if constexpr (kLn) {
+                ls1[i] += (a.x + a.y) + (a.z + a.w);
+                ls2[i] = fmaf(a.x, a.x, fmaf(a.y, a.y, fmaf(a.z, a.z, fmaf(a.w, a.w, ls2[i]))));
               }
               if constexpr (EPI == EPI_CONV_RELU_MASK_F32) {
                 const bool lv = r < rows_live;
@@ -282,6 +458,13 @@ gemm2_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             }
           }
           __syncwarp();
+        }
+        if constexpr (kLn) {
+          // the accumulator is drained: hand it back to the MMA warp before the cross-CTA exchange below
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive_cluster(&tmem_empty[acc], 0);
+          ln_tail(p, ls1, ls2, warp_row0, rows_valid, m_blk * 4 + quad, n_blk, half, lane);
         }
       } else if constexpr (EPI == EPI_POWER_F32) {
         // |X|^2 of a DFT whose cos rows fill accumulator columns [0,128) and sin rows [128,256) of the tile
@@ -390,9 +573,11 @@ gemm2_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           __syncwarp();
         }
       }
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive_cluster(&tmem_empty[acc], 0);
+      if constexpr (EPI != EPI_BIAS_RES_LN_F32) {
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive_cluster(&tmem_empty[acc], 0);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }

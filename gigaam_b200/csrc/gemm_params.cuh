@@ -1,0 +1,103 @@
+// Shared definitions of the tcgen05 GEMM (gemm2_sm100.cuh): epilogue / A-operand modes, the parameter block, and the
+// small math helpers of the fused epilogues.
+//
+//   * A and W are fp16, K-contiguous ("TN"): exactly the layout of an activation matrix [rows, feat]
+//     and of an nn.Linear / Conv1d(k=1) weight [out, in] (reference: gigaam/encoder.py:145-148,
+//     378,393,418-420), so no operand is ever transposed in memory.
+//   * A_CONV mode: the A operand is the implicit im2col of a channels-last activation
+//     [B, T1, F1, C] for a 3x3 / stride-2 / pad-1 convolution (reference: gigaam/encoder.py:59-70),
+//     fetched tap by tap with a 4-D strided TMA box (elementStrides = 2 on T and F, OOB = zero fill
+//     = the conv's zero padding).  Nothing is ever materialised as an im2col matrix.
+#pragma once
+#include "ptx.cuh"
+
+namespace gam {
+
+enum GemmEpilogue : int {
+  EPI_BIAS_F16 = 0,        // out16 = acc + bias
+  EPI_BIAS_SILU_F16 = 1,   // out16 = silu(acc + bias)
+  EPI_BIAS_GLU_F16 = 2,    // out16[:, n] = (acc_a + bias_a) * sigmoid(acc_b + bias_b), tile = [a|b]
+  EPI_BIAS_RES_F32 = 3,    // out32 = res + scale * (acc + bias)
+  EPI_BIAS_F32 = 4,        // out32 = acc + bias
+  EPI_CONV_RELU_MASK_F16 = 5,  // out16 = t2 < len2[b] ? relu(acc + bias) : 0   (A_CONV / A_CONV1D row mapping)
+  EPI_CONV_RELU_MASK_F32 = 6,  // out32 = t < len[b] ? relu(acc + bias) : 0      (A_CONV1D, last subsampling stage)
+  EPI_POWER_F32 = 7,           // out32[:, n] = re^2 + im^2, tile = [128 re | 128 im]  (DFT power spectrum, no bias)
+  EPI_BIAS_RES_LN_F32 = 8,     // EPI_BIAS_RES_F32 + the LayerNorm(s) that follow it in the layer, see LnFuse
+};
+
+// LayerNorm fused behind the residual epilogue of an N = 768 GEMM (gigaam/encoder.py:481-497: every residual add of a
+// Conformer layer is followed by a LayerNorm of the full 768-wide row, whose fp16 result is the next GEMM's A operand).
+// A 256 x 256 tile sees a third of a row, so the row statistics are exchanged through global memory: every epilogue warp
+// writes (sum, sum of squares) of its 32 rows x 128 columns into its own slot (fixed slots, fixed summation order:
+// deterministic), bumps a per-32-row counter with release semantics, waits until the six slots of its rows have
+// arrived, and normalises the values it has just written (re-read from L2).  Needs all CTAs of the grid co-resident
+// (persistent grid <= #SMs, 1 CTA / SM: true for every launch of this kernel).
+//   mode 1: out16 = LN(x)                                  norm_conv, norm_feed_forward2 (and norm_self_att for rel_pos)
+//   mode 2: out16 = u = LN(x), rope16 = rope(u)            norm_self_att of the rotary models (utils.py:83-100)
+//   mode 3: xout = LN(x) fp32; out16 = LN2(xout) if g2     norm_out (+ the next layer's norm_feed_forward1)
+struct LnFuse {
+  int mode;                    // 0 = off
+  const float *g, *b;          // first LayerNorm affine [768]
+  const float *g2, *b2;        // mode 3: second LayerNorm affine, or null (last layer)
+  __half* out16;               // [M, 768]
+  __half* rope16;              // mode 2
+  float* xout;                 // mode 3 (may alias the GEMM output)
+  float2* stats;               // [M_pad, 6] partial (sum, sumsq): slot = 2 * n_tile + column half
+  float2* stats2;              // mode 3, second round
+  unsigned int* cnt;           // [M_pad / 32] arrivals per 32-row group, zero on entry
+  unsigned int* cnt2;          // mode 3, second round
+  const float *rope_cos, *rope_sin;   // [max_len, half_dim]
+  int T, half_dim;
+  float eps;
+};
+
+// A_CONV  : implicit im2col of a 3x3 / stride-2 conv2d over channels-last [B, T1, F1, C]  (4-D strided TMA)
+// A_CONV1D: implicit im2col of a k-tap / stride-2 conv1d over time-major [B, T_in, C]      (3-D strided TMA);
+//           a 128-row block = 128 consecutive output frames of one utterance
+enum GemmAMode : int { A_2D = 0, A_CONV = 1, A_CONV1D = 2 };
+
+struct GemmParams {
+  int M;             // valid rows of D (A_2D) ; unused for A_CONV
+  int N;             // columns of the accumulator matrix (= rows of W)
+  int num_m_tiles;
+  int num_n_tiles;
+  int num_k_blocks;  // K / 64   (A_CONV: 9 taps * C/64)
+  const float* bias;  // [N] in accumulator column order
+  const float* res;   // fp32 residual, row pitch ldo (EPI_BIAS_RES_F32)
+  void* out;
+  int ldo;            // output row pitch in elements
+  float scale;
+  // A_CONV only
+  int conv_T2;            // output time steps per utterance
+  int conv_tiles_per_utt; // ceil(T2 / 8)
+  int conv_kchunks;       // C / 64
+  int conv_num_blocks;    // B * conv_tiles_per_utt  (128-row blocks that exist)
+  int conv_pad;           // A_CONV1D: (taps - 1) / 2
+  const int* conv_len2;   // [B] valid output time steps
+  // pair kernel, A_2D only: n-tiles [0, a1_nblks) read A through tmap_a, the rest through tmap_a2 (0 = tmap_a for all).
+  // Lets two GEMMs that share M, K and the output buffer but not the A operand (W_qk on rope(u), W_v on u) run as one launch.
+  int a1_nblks;
+  LnFuse ln;   // EPI_BIAS_RES_LN_F32
+};
+
+constexpr int kGemmBM = 128;
+constexpr int kGemmBK = 64;
+__device__ __forceinline__ float fast_tanh(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// silu(x) = x * sigmoid(x) = 0.5x * (1 + tanh(0.5x))
+__device__ __forceinline__ float silu_f(float x) {
+  float h = 0.5f * x;
+  return fmaf(h, fast_tanh(h), h);
+}
+__device__ __forceinline__ float sigmoid_f(float x) { return fmaf(0.5f, fast_tanh(0.5f * x), 0.5f); }
+
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+
+}  // namespace gam

@@ -29,11 +29,11 @@ int launch_subsample_conv1(const float* mel, const int* len0, const int* len1, c
 
 // attention_sm100.cu
 int launch_attention(const CUtensorMap* tmap_qkv, const int* klen, __half* out, int B, int T, int H, int dk, int d_model,
-                     cudaStream_t s);
+                     int num_sms, cudaStream_t s);
 
 // attention_relpos_sm100.cu: qkv [B*T, 4*d_model] = [q+u | q+v | k | v]; pos = projected position table of
 // 2*kRelPosMaxT-1 rows (GAM_REL_POS_MAX_T in the public header)
-constexpr int kRelPosMaxT = 640;
+constexpr int kRelPosMaxT = 768;
 int launch_attention_relpos(const CUtensorMap* tmap_qkv, const CUtensorMap* tmap_pos, const int* klen, __half* out, int B, int T,
                             int H, int dk, int d_model, cudaStream_t s);
 
@@ -45,17 +45,15 @@ void launch_ctc_collapse(const int* labels, const int* len, int B, int T, int bl
 
 // rnnt.cu
 void launch_sgemm_tn_bias(const float* A, const float* W, const float* bias, float* C, int M, int N, int K, cudaStream_t s);
-int launch_rnnt_greedy(const float* encproj, const int* len, const float* emb_gates, const float* whhT, const float* wpT,
-                       const float* bp, const float* wo, const float* bo, int B, int T, int H, int V1, int blank,
-                       int max_symbols, int max_out, int* ids, int* frames, int* counts, cudaStream_t s);
 
-// rnnt_cluster.cu: returns 0 ok, 1 = 16-CTA clusters unavailable / unsupported shape (use launch_rnnt_greedy), <0 error
+// rnnt_cluster.cu: returns 0 ok, 1 = 16-CTA clusters unavailable / unsupported shape, <0 error
 int launch_rnnt_greedy_cluster(const float* encproj, const int* len, const float* emb_gates, const float* whhT, const float* wpT,
                                const float* bp, const float* wo, const float* bo, int B, int T, int H, int V1, int blank,
                                int max_symbols, int max_out, int* ids, int* frames, int* counts, cudaStream_t s);
 
 // gemm.cu
 struct GemmParams;
+struct LnFuse;
 enum GemmKind : int {
   GEMM_BIAS_F16 = 0,
   GEMM_BIAS_SILU_F16 = 1,
@@ -67,8 +65,11 @@ enum GemmKind : int {
 // 2-D operand GEMM  D[M,N] = A[M,K] W[N,K]^T with fused epilogue `kind`; N % 256 == 0, K % 64 == 0.
 int launch_gemm(int kind, const CUtensorMap* tmap_a, const CUtensorMap* tmap_w, int M, int N, int K, const float* bias,
                 const float* res, void* out, int ldo, float scale, int num_sms, cudaStream_t s);
+// x = res + scale * (A W^T + bias) with the following LayerNorm(s) fused behind it (gemm_params.cuh: LnFuse); N = 768
+int launch_gemm_res_ln(const CUtensorMap* tmap_a, const CUtensorMap* tmap_w, int M, int K, const float* bias, const float* res,
+                       float* out, float scale, const LnFuse& ln, int num_sms, cudaStream_t s);
 // one launch for two GEMMs that share M, K, W's row space and the output buffer but read different A operands:
-// columns [0, n1) from tmap_a1, [n1, N) from tmap_a2 (bias -> fp16).  Returns -1 when the single-CTA kernel is forced.
+// columns [0, n1) from tmap_a1, [n1, N) from tmap_a2 (bias -> fp16).  
 int launch_gemm_dual_a(const CUtensorMap* tmap_a1, const CUtensorMap* tmap_a2, int n1, const CUtensorMap* tmap_w, int M, int N,
                        int K, const float* bias, void* out, int ldo, int num_sms, cudaStream_t s);
 // implicit-GEMM 3x3/s2 conv over channels-last [B,T1,F1,C] (tmap_a 4-D strided), output [B*T2*16, N] fp16

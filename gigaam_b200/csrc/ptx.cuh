@@ -32,14 +32,6 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
-// ---------------------------------------------------------------- programmatic dependent launch
-// Every kernel of the path is launched with programmaticStreamSerializationAllowed (launch.cuh): it lets its
-// dependents be scheduled as soon as SMs free up (launch_dependents, first instruction) and blocks before its first
-// global-memory access until the kernel it depends on has completed and flushed (wait).  Barrier init, TMEM
-// allocation and descriptor prefetch therefore overlap the predecessor's tail.  No-ops without the attribute.
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

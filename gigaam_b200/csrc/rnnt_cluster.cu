@@ -630,13 +630,14 @@ extern "C" int gam_rnnt_debug_read(long long* out16) {
 }
 #endif
 
-// returns 0 on success, 1 if a 16-CTA cluster cannot be scheduled on this device (caller falls back to the
-// per-utterance kernel), negative on error
+// returns 0 on success, 1 if the shape is unsupported (pred_hidden != 320) or a 16-CTA cluster cannot be scheduled on
+// this device, negative on a launch error
 int launch_rnnt_greedy_cluster(const float* encproj, const int* len, const float* emb_gates, const float* whhT, const float* wpT,
                                const float* bp, const float* wo, const float* bo, int B, int T, int H, int V1, int blank,
                                int max_symbols, int max_out, int* ids, int* frames, int* counts, cudaStream_t s) {
   if (H != kH) return 1;
-  static int smem_cap = 0, clusters_hint = 0, info = -1;
+  static int smem_cap = 0, clusters_hint = 0;
+  constexpr int info = 0;
   if (smem_cap == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -645,8 +646,6 @@ int launch_rnnt_greedy_cluster(const float* encproj, const int* len, const float
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     clusters_hint = sms / kCl - 2;   // GPCs rarely hold more than one 16-CTA cluster each (7 on a 148-SM B200)
     if (clusters_hint < 1) clusters_hint = 1;
-    const char* e = getenv("GAM_RNNT_INFO");
-    info = (e && e[0] == '1') ? 1 : 0;
   }
   RnntClParams p;
   p.encproj = encproj; p.len = len; p.emb_gates = emb_gates; p.whhT = whhT; p.wpT = wpT; p.bp = bp; p.wo = wo; p.bo = bo;

@@ -57,8 +57,6 @@ __device__ __forceinline__ uint2 pack4(float4 v) {
 __global__ void __launch_bounds__(256) ln_f16_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                      const float* __restrict__ beta, __half* __restrict__ out,
                                                      int rows, float eps) {
-  ptx::pdl_launch_dependents();
-  ptx::pdl_wait();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -83,8 +81,6 @@ __global__ void __launch_bounds__(256) ln_rope_f16_kernel(const float* __restric
                                                           __half* __restrict__ out_r, int rows, int T, int half_dim,
                                                           float eps) {
   __shared__ float srow[8][kD];
-  ptx::pdl_launch_dependents();
-  ptx::pdl_wait();
   const int lane = threadIdx.x & 31;
   const int w = threadIdx.x >> 5;
   const int row = blockIdx.x * 8 + w;
@@ -130,8 +126,6 @@ __global__ void __launch_bounds__(256) ln_out_ln_kernel(const float* __restrict_
                                                         const float* __restrict__ b_out, const float* __restrict__ g_next,
                                                         const float* __restrict__ b_next, float* __restrict__ x_out,
                                                         __half* __restrict__ y_out, int rows, float eps) {
-  ptx::pdl_launch_dependents();
-  ptx::pdl_wait();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -179,8 +173,6 @@ __global__ void __launch_bounds__(256) dwconv_bn_silu_kernel(const __half* __res
   constexpr int kHalo = (KW - 1) / 2;
   constexpr int kRows = kDwTT + KW - 1;
   __shared__ __align__(16) __half2 tile[kRows][kDwCT / 2];
-  ptx::pdl_launch_dependents();
-  ptx::pdl_wait();
   const int c0 = blockIdx.x * kDwCT;
   const int t0 = blockIdx.y * kDwTT;
   const int b = blockIdx.z;
@@ -297,21 +289,21 @@ __global__ void sub_lengths_kernel(const long long* __restrict__ mel_len, int B,
 
 // ------------------------------------------------------------------ launchers
 void launch_ln_f16(const float* x, const float* g, const float* b, __half* out, int rows, cudaStream_t s) {
-  launch_pdl(ln_f16_kernel, dim3((rows + 7) / 8), dim3(256), 0, s, x, g, b, out, rows, 1e-5f);
+  launch_k(ln_f16_kernel, dim3((rows + 7) / 8), dim3(256), 0, s, x, g, b, out, rows, 1e-5f);
 }
 void launch_ln_rope_f16(const float* x, const float* g, const float* b, const float* rc, const float* rs, __half* out_u,
                         __half* out_r, int rows, int T, int half_dim, cudaStream_t s) {
-  launch_pdl(ln_rope_f16_kernel, dim3((rows + 7) / 8), dim3(256), 0, s, x, g, b, rc, rs, out_u, out_r, rows, T, half_dim, 1e-5f);
+  launch_k(ln_rope_f16_kernel, dim3((rows + 7) / 8), dim3(256), 0, s, x, g, b, rc, rs, out_u, out_r, rows, T, half_dim, 1e-5f);
 }
 void launch_ln_out_ln(const float* r, const float* g_out, const float* b_out, const float* g_next, const float* b_next,
                       float* x_out, __half* y_out, int rows, cudaStream_t s) {
-  launch_pdl(ln_out_ln_kernel, dim3((rows + 7) / 8), dim3(256), 0, s, r, g_out, b_out, g_next, b_next, x_out, y_out, rows, 1e-5f);
+  launch_k(ln_out_ln_kernel, dim3((rows + 7) / 8), dim3(256), 0, s, r, g_out, b_out, g_next, b_next, x_out, y_out, rows, 1e-5f);
 }
 int launch_dwconv_bn_silu(const __half* g, const float* w, const float* bias, const int* len, __half* out, int B, int T,
                           int kw, cudaStream_t s) {
   dim3 grid(kD / kDwCT, (T + kDwTT - 1) / kDwTT, B);
-  if (kw == 31) launch_pdl(dwconv_bn_silu_kernel<31>, grid, dim3(256), 0, s, g, w, bias, len, out, T);
-  else if (kw == 5) launch_pdl(dwconv_bn_silu_kernel<5>, grid, dim3(256), 0, s, g, w, bias, len, out, T);
+  if (kw == 31) launch_k(dwconv_bn_silu_kernel<31>, grid, dim3(256), 0, s, g, w, bias, len, out, T);
+  else if (kw == 5) launch_k(dwconv_bn_silu_kernel<5>, grid, dim3(256), 0, s, g, w, bias, len, out, T);
   else return -1;
   return 0;
 }

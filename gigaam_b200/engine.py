@@ -4,9 +4,9 @@ done here -- only one-off weight re-layout at load time (BatchNorm folding, q/k 
 conv weight permutation, fp16 casts, DFT / rotary tables)."""
 from __future__ import annotations
 
+import collections
 import ctypes as C
 import math
-import os
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -98,17 +98,49 @@ def rotary_half_tables(dk: int, base: float, max_len: int):
     return freqs.cos(), freqs.sin()
 
 
+class _WorkspaceCache:
+    """Bounded LRU of scratch tensors of ONE kind (encode / log-mel / decode).  Eviction only drops this cache's
+    reference: a CUDA graph that baked a workspace pointer keeps the tensor alive through `Engine.held_workspaces`."""
+
+    def __init__(self, cap: int):
+        self.cap = cap
+        self._d: "collections.OrderedDict[Tuple, Tensor]" = collections.OrderedDict()
+
+    def get(self, key, nbytes: int, device) -> Tensor:
+        ws = self._d.get(key)
+        if ws is not None and ws.numel() >= nbytes:
+            self._d.move_to_end(key)
+            return ws
+        while len(self._d) >= self.cap:
+            self._d.popitem(last=False)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        self._d[key] = ws
+        return ws
+
+    def peek(self, key) -> Optional[Tensor]:
+        return self._d.get(key)
+
+    def __len__(self):
+        return len(self._d)
+
+
 class Engine:
     """One model replica on one CUDA device."""
+
+    WS_CACHE = 4      # workspaces kept per kind (distinct batch shapes)
 
     def __init__(self, cfg: Dict, state_dict: Dict[str, Tensor], device: torch.device):
         if device.type != "cuda":
             raise RuntimeError("gigaam_b200 runs on CUDA (sm_100a) devices only; there is no CPU path")
+        if device.index is None:      # an index-less "cuda" means the CURRENT device, not GPU 0
+            device = torch.device("cuda", torch.cuda.current_device())
         self.lib = _lib.load()
         self.device = device
         self.cfg = cfg
         self._keep: List[Tensor] = []
-        self._ws: Dict[Tuple[int, int], Tensor] = {}
+        self._ws_enc = _WorkspaceCache(self.WS_CACHE)
+        self._ws_mel = _WorkspaceCache(self.WS_CACHE)
+        self._ws_dec = _WorkspaceCache(self.WS_CACHE)
         self.handle = C.c_void_p()
         pre, enc = cfg["preprocessor"], cfg["encoder"]
         head = cfg.get("head") if isinstance(cfg, dict) else None
@@ -157,7 +189,7 @@ class Engine:
                 self.max_symbols = int(_cfg_get(cfg.get("decoding", {}), "max_symbols_per_step", 10))
         gc.head, gc.num_classes, gc.max_symbols = self.head_type, self.num_classes, self.max_symbols
         with torch.cuda.device(device):
-            rc = self.lib.gam_create(C.byref(gc), C.byref(gw), device.index or 0, C.byref(self.handle))
+            rc = self.lib.gam_create(C.byref(gc), C.byref(gw), device.index, C.byref(self.handle))
         _lib.check(self.lib, self.handle, rc, "gam_create")
 
     # ------------------------------------------------------------------ packing helpers
@@ -280,7 +312,10 @@ class Engine:
             raise NotImplementedError("multi-layer prediction LSTM")
         self.head_type, self.num_classes = 2, jt["num_classes"]
         gc.pred_hidden, gc.joint_hidden = dc["pred_hidden"], jt["joint_hidden"]
-        emb = sd["head.decoder.embed.weight"].double()
+        emb = sd["head.decoder.embed.weight"].double().clone()
+        # predict(None, None) starts from an all-zero embedding (gigaam/decoder.py:92-95) and nn.Embedding's padding_idx
+        # row is zero by construction but not enforced by load_state_dict: the table's blank row carries the biases only
+        emb[jt["num_classes"] - 1].zero_()
         w_ih, w_hh = sd["head.decoder.lstm.weight_ih_l0"].double(), sd["head.decoder.lstm.weight_hh_l0"].float()
         bias = sd["head.decoder.lstm.bias_ih_l0"].double() + sd["head.decoder.lstm.bias_hh_l0"].double()
         gw.rnnt_emb_gates = self._dev((emb @ w_ih.t() + bias).float())
@@ -303,33 +338,31 @@ class Engine:
         return int(self.lib.gam_encoded_frames(self.handle, int(m)))
 
     def workspace(self, B: int, M: int) -> Tensor:
-        key = (B, M)
-        ws = self._ws.get(key)
-        if ws is None:
-            nbytes = int(self.lib.gam_workspace_bytes(self.handle, B, M))
-            if len(self._ws) >= 4:
-                self._ws.pop(next(iter(self._ws)))
-            ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
-            self._ws[key] = ws
-        return ws
+        return self._ws_enc.get((B, M), int(self.lib.gam_workspace_bytes(self.handle, B, M)), self.device)
 
-    def logmel(self, wav: Tensor) -> Tensor:
-        """[B, N] f32 on device -> [B, n_mels, M] f32 (FeatureExtractor.forward, gigaam/preprocess.py:94-98)"""
+    def held_workspaces(self, B: int, N: int) -> List[Tensor]:
+        """The scratch tensors a step over a [B, N] waveform batch touches.  A captured CUDA graph stores this list: the
+        pointers it baked stay valid however many other shapes pass through the engine afterwards."""
+        M = self.logmel_frames(N)
+        T = self.encoded_frames(M)
+        held = [self._ws_mel.peek((B, N)), self._ws_enc.peek((B, M)), self._ws_dec.peek((B, T))]
+        return [t for t in held if t is not None]
+
+    def logmel(self, wav: Tensor, fused: bool = False) -> Tensor:
+        """[B, N] f32 on device -> [B, n_mels, M] f32 (FeatureExtractor.forward, gigaam/preprocess.py:94-98).
+        `fused=True` selects the single CUDA-core kernel (no workspace) instead of the tensor-core DFT."""
         assert wav.is_cuda and wav.dtype == torch.float32 and wav.dim() == 2
         wav = wav.contiguous()
         B, N = wav.shape
         M = self.logmel_frames(N)
         mel = torch.empty((B, self.n_mels, M), dtype=torch.float32, device=self.device)
-        if self._logmel_tc and os.environ.get("GAM_LOGMEL_FUSED", "0") != "1":
-            key = ("logmel", B, N)
-            ws = self._ws.get(key)
-            if ws is None:
-                ws = torch.empty(int(self.lib.gam_logmel_workspace_bytes(self.handle, B, N)), dtype=torch.uint8, device=self.device)
-                self._ws[key] = ws
-            rc = self.lib.gam_logmel_tc(self.handle, wav.data_ptr(), B, N, mel.data_ptr(), ws.data_ptr(), ws.numel(), self._stream())
-            _lib.check(self.lib, self.handle, rc, "gam_logmel_tc")
-            return mel
-        rc = self.lib.gam_logmel(self.handle, wav.data_ptr(), B, N, mel.data_ptr(), self._stream())
+        with torch.cuda.device(self.device):
+            if self._logmel_tc and not fused:
+                ws = self._ws_mel.get((B, N), int(self.lib.gam_logmel_workspace_bytes(self.handle, B, N)), self.device)
+                rc = self.lib.gam_logmel_tc(self.handle, wav.data_ptr(), B, N, mel.data_ptr(), ws.data_ptr(), ws.numel(), self._stream())
+                _lib.check(self.lib, self.handle, rc, "gam_logmel_tc")
+                return mel
+            rc = self.lib.gam_logmel(self.handle, wav.data_ptr(), B, N, mel.data_ptr(), self._stream())
         _lib.check(self.lib, self.handle, rc, "gam_logmel")
         return mel
 
@@ -343,35 +376,28 @@ class Engine:
         ws = self.workspace(B, M)
         enc = torch.empty((B, T, self.d_model), dtype=torch.float32, device=self.device)
         enc_len = torch.empty((B,), dtype=torch.int32, device=self.device)
-        rc = self.lib.gam_encode(self.handle, mel.data_ptr(), mel_len.data_ptr(), B, M, ws.data_ptr(), ws.numel(),
-                                 enc.data_ptr(), enc_len.data_ptr(), n_layers_run, self._stream())
+        with torch.cuda.device(self.device):
+            rc = self.lib.gam_encode(self.handle, mel.data_ptr(), mel_len.data_ptr(), B, M, ws.data_ptr(), ws.numel(),
+                                     enc.data_ptr(), enc_len.data_ptr(), n_layers_run, self._stream())
         _lib.check(self.lib, self.handle, rc, "gam_encode")
         return enc, enc_len
-
-    def _decode_ws(self, B: int, T: int) -> Tensor:
-        need = B * T * 4 * max(1, 320) + 4096
-        key = (-B, T)
-        ws = self._ws.get(key)
-        if ws is None or ws.numel() < need:
-            ws = torch.empty(need, dtype=torch.uint8, device=self.device)
-            self._ws[key] = ws
-        return ws
 
     def greedy(self, enc_btd: Tensor, enc_len: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
         """enc [B, T, d] f32 contiguous, len [B] -> (ids [B, max_out] i32, frames, counts [B] i32) on device."""
         assert enc_btd.is_cuda and enc_btd.dtype == torch.float32 and enc_btd.is_contiguous()
+        if self.head_type == 0:
+            raise RuntimeError("model has no head to decode with")
         B, T, _ = enc_btd.shape
         enc_len = enc_len.to(device=self.device, dtype=torch.int32).contiguous()
         max_out = T if self.head_type == 1 else T * self.max_symbols
         ids = torch.empty((B, max_out), dtype=torch.int32, device=self.device)
         frames = torch.empty((B, max_out), dtype=torch.int32, device=self.device)
         counts = torch.empty((B,), dtype=torch.int32, device=self.device)
-        ws = self._decode_ws(B, T)
+        ws = self._ws_dec.get((B, T), int(self.lib.gam_decode_workspace_bytes(self.handle, B, T)), self.device)
         fn = self.lib.gam_ctc_greedy if self.head_type == 1 else self.lib.gam_rnnt_greedy
-        if self.head_type == 0:
-            raise RuntimeError("model has no head to decode with")
-        rc = fn(self.handle, enc_btd.data_ptr(), enc_len.data_ptr(), B, T, ws.data_ptr(), ws.numel(), ids.data_ptr(),
-                frames.data_ptr(), counts.data_ptr(), max_out, self._stream())
+        with torch.cuda.device(self.device):
+            rc = fn(self.handle, enc_btd.data_ptr(), enc_len.data_ptr(), B, T, ws.data_ptr(), ws.numel(), ids.data_ptr(),
+                    frames.data_ptr(), counts.data_ptr(), max_out, self._stream())
         _lib.check(self.lib, self.handle, rc, "gam_greedy")
         return ids, frames, counts
 

@@ -29,6 +29,9 @@ class _ShapeGraph:
         with torch.cuda.graph(self.graph, stream=side):
             self.out = self._step(model)
         torch.cuda.current_stream(dev).wait_stream(side)
+        # the graph baked the pointers of the engine's scratch buffers for this shape: own them, so the engine's
+        # per-kind LRU may forget the shape without freeing memory this graph still writes
+        self._held = model._get_engine().held_workspaces(B, N)
 
     def _step(self, model):
         enc, enc_len = model(self.wav, self.len)

@@ -11,7 +11,8 @@ randomised so that BN folding is actually exercised.
 from __future__ import annotations
 
 import math
-from typing import Dict, List, Tuple
+from pathlib import Path
+from typing import Dict, List, Optional, Tuple
 
 import numpy as np
 import torch
@@ -21,9 +22,17 @@ SAMPLE_RATE = 16000
 _CHAR_VOCAB = [" "] + [chr(c) for c in range(ord("а"), ord("я") + 1)]  # 33 symbols -> V+1 = 34
 assert len(_CHAR_VOCAB) == 33
 
-# blank-logit bias added to head.joint.joint_net.1.bias[blank]; calibrated with oracle/calibrate_rnnt.py
-# (random weights otherwise emit max_symbols tokens on every frame).
-RNNT_BLANK_BIAS = {"v2_rnnt": 7.45, "v3_e2e_rnnt": 23.3, "v3_rnnt": 7.45}
+# Per-model calibration of the synthetic RNN-T joint network, written by oracle/calibrate_rnnt.py (random weights
+# otherwise emit max_symbols tokens on every frame or none at all): the mean encoder frame that
+# `head.joint.enc.bias` cancels and the blank-logit bias that lands the token rate on BASELINE.md's target.
+RNNT_CALIBRATION_FILE = Path(__file__).with_name("rnnt_calibration.npz")
+
+
+def _rnnt_calibration(model_name: str) -> Dict:
+    if not RNNT_CALIBRATION_FILE.exists():
+        return {}
+    with np.load(RNNT_CALIBRATION_FILE) as z:
+        return {k.split("/", 1)[1]: z[k] for k in z.files if k.startswith(model_name + "/")}
 
 
 def _encoder_cfg(version: str) -> Dict:
@@ -93,7 +102,7 @@ def mel_filterbank(n_freqs: int, n_mels: int, sample_rate: int) -> torch.Tensor:
 # Random heads are nearly input-independent (every frame gives the same argmax); these gains make the joint
 # network's logits depend on the frame and on the prediction-network state so that greedy decoding is not a
 # degenerate all-or-nothing function of the blank bias.
-_GAIN = {"head.joint.joint_net.1.weight": 6.0, "head.joint.enc.weight": 3.0, "head.joint.pred.weight": 3.0,
+_GAIN = {"head.joint.joint_net.1.weight": 6.0, "head.joint.enc.weight": 20.0, "head.joint.pred.weight": 10.0,
          "head.decoder_layers.0.weight": 4.0}
 
 def _param_list(cfg: Dict) -> List[Tuple[str, Tuple[int, ...], str, float]]:
@@ -194,8 +203,9 @@ def head_param_list(head) -> List[Tuple[str, Tuple[int, ...], str, float]]:
     return out
 
 
-def synthetic_state_dict(cfg: Dict, seed: int = 0) -> Dict[str, torch.Tensor]:
-    """Seeded fp32 state_dict with the reference's key names and shapes."""
+def synthetic_state_dict(cfg: Dict, seed: int = 0, rnnt_calibration: Optional[Dict] = None) -> Dict[str, torch.Tensor]:
+    """Seeded fp32 state_dict with the reference's key names and shapes.  `rnnt_calibration` overrides the stored
+    calibration of an RNN-T head (`{}` = none: what oracle/calibrate_rnnt.py starts from)."""
     gen = torch.Generator(device="cpu")
     gen.manual_seed(seed)
     sd: Dict[str, torch.Tensor] = {}
@@ -228,14 +238,17 @@ def synthetic_state_dict(cfg: Dict, seed: int = 0) -> Dict[str, torch.Tensor]:
         sd[key] = t * _GAIN.get(key, 1.0)
     head = cfg.get("head")
     if head and head["type"] == "rnnt":
-        bias = RNNT_BLANK_BIAS.get(cfg["model_name"], 1.0)
-        sd["head.joint.joint_net.1.bias"][-1] += bias
+        cal = _rnnt_calibration(cfg["model_name"]) if rnnt_calibration is None else rnnt_calibration
+        if "enc_mean" in cal:
+            sd["head.joint.enc.bias"] = -(sd["head.joint.enc.weight"] @ torch.as_tensor(cal["enc_mean"]))
+        sd["head.joint.joint_net.1.bias"][-1] += float(cal.get("blank_bias", 0.0))
     return sd
 
 
-def synthetic_checkpoint(model_name: str, seed: int = 0, n_layers: int | None = None) -> Dict:
+def synthetic_checkpoint(model_name: str, seed: int = 0, n_layers: int | None = None,
+                         rnnt_calibration: Optional[Dict] = None) -> Dict:
     cfg = model_cfg(model_name, n_layers)
-    return {"cfg": cfg, "state_dict": synthetic_state_dict(cfg, seed)}
+    return {"cfg": cfg, "state_dict": synthetic_state_dict(cfg, seed, rnnt_calibration)}
 
 
 # ------------------------------------------------------------------------------------------ audio

@@ -81,7 +81,7 @@ typedef struct gam_layer_weights {
                            * position r (pe = gigaam/encoder.py:318-326) */
 } gam_layer_weights;
 
-#define GAM_REL_POS_MAX_T 640 /* longest T' the rel_pos attention kernel serves (5 key blocks of 128) */
+#define GAM_REL_POS_MAX_T 768 /* longest T' the attention kernels serve (6 key blocks of 128 = 30.7 s of audio) */
 
 typedef struct gam_weights {
   /* front end */
@@ -137,6 +137,9 @@ int64_t gam_encoded_frames(const gam_handle* h, int64_t mel_frames);
 /* bytes of scratch gam_encode / gam_*_greedy need for a batch of B utterances of M mel frames */
 int64_t gam_workspace_bytes(const gam_handle* h, int32_t B, int64_t mel_frames);
 
+/* bytes of scratch gam_ctc_greedy / gam_rnnt_greedy need on their own (B utterances of T encoder frames) */
+int64_t gam_decode_workspace_bytes(const gam_handle* h, int32_t B, int32_t T);
+
 /* wav: device f32 [B, n_samples]  ->  mel: device f32 [B, n_mels, M] */
 int gam_logmel(gam_handle* h, const float* wav, int32_t B, int64_t n_samples, float* mel, void* stream);
 
@@ -167,6 +170,14 @@ int gam_rnnt_greedy(gam_handle* h, const float* enc, const int32_t* enc_len, int
  * 3 res + scale*(acc+bias) -> f32, 4 bias -> f32).  A, W fp16 device; N % 256 == 0; K % 64 == 0. */
 int gam_test_gemm(gam_handle* h, int32_t kind, const void* A, const void* W, const float* bias, const float* res, void* out,
                   int32_t M, int32_t N, int32_t K, int32_t ldo, float scale, void* stream);
+/* The residual GEMM of a Conformer layer with the LayerNorm(s) that follow it fused behind the epilogue
+ * (gigaam/encoder.py:481-497): x[M,768] += scale * (A[M,K] W[768,K]^T + bias) in place, then
+ *   mode 1: out16 = LN(x; g, b)                      mode 2: out16 = u = LN(x; g, b), rope16 = rotary(u) with t = row % T
+ *   mode 3: xout = LN(x; g, b) fp32 (may alias x); out16 = LN(xout; g2, b2) unless g2 == NULL
+ * workspace: >= 2 * align1024(M * 48) + 2 * ceil(M / 256) * 32 bytes. */
+int gam_test_gemm_ln(gam_handle* h, int32_t mode, const void* A, const void* W, const float* bias, float* x, const float* g,
+                     const float* b, const float* g2, const float* b2, void* out16, void* rope16, float* xout, int32_t M, int32_t K,
+                     int32_t T, float scale, void* workspace, int64_t workspace_bytes, void* stream);
 /* qkv: f16 [B*T, 3*d_model]; klen i32 [B] or NULL -> out f16 [B*T, d_model] */
 int gam_test_attention(gam_handle* h, const void* qkv, const int32_t* klen, void* out, int32_t B, int32_t T, void* stream);
 /* rel_pos variant: qkv f16 [B*T, 4*d_model] = [q+u | q+v | k | v]; pos f16 [2*GAM_REL_POS_MAX_T-1, d_model] */

@@ -1,47 +1,99 @@
-"""Calibrate the synthetic RNN-T blank bias (gigaam_b200/synthetic.py:RNNT_BLANK_BIAS) by bisection so the
-seeded random head emits a realistic token rate (~0.5 tok/frame at V+1=34, ~0.2 at V+1=1025).
-Test infrastructure: runs the oracle on CPU.   python oracle/calibrate_rnnt.py v2_rnnt 0.5
+"""Calibrate the synthetic RNN-T heads (gigaam_b200/synthetic.py) so the seeded random joint network emits a realistic
+token rate on the benchmark audio (~0.5 tokens/frame at V+1 = 34, ~0.2 at V+1 = 1025).
+Test infrastructure: runs the oracle on CPU and writes gigaam_b200/rnnt_calibration.npz.
+
+    python oracle/calibrate_rnnt.py                 # all RNN-T model names
+    python oracle/calibrate_rnnt.py v3_e2e_rnnt     # one of them
+
+Why a blank bias alone cannot do it (round-1 finding: 3.25 tokens/frame in bursts at V+1 = 1025): the synthetic
+test signal is stationary, so the encoder frames of an utterance are almost identical (std over time 0.07 against
+1.0 overall) and a joint network with random weights decides once per utterance -- every frame emits max_symbols
+tokens, or none does, and the rate is a cliff in the bias.  Two more free parameters of the head are therefore set:
+
+  * `head.joint.enc.bias` = -W_e * mean encoder frame of the calibration audio: the joint sees the frame-to-frame
+    VARIATION of the encoder output instead of its constant part;
+  * gains on the three joint matrices (enc 20, pred 10, out 6 times the default uniform init) so that this variation
+    and the prediction-network state both move the logits;
+
+then the blank-logit bias is found by bisection on the token rate.  Every utterance emits, frames mix blanks,
+single tokens and bursts up to max_symbols, and the rate is smooth in the bias (reported below).
 """
 from __future__ import annotations
 
+import collections
 import sys
 from pathlib import Path
 
+import numpy as np
 import torch
 
 ROOT = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT))
 
+TARGETS = {"v2_rnnt": 0.5, "v3_rnnt": 0.5, "v3_e2e_rnnt": 0.2}
+# (batch, seconds, audio seed, ragged): the audio of the golden fixtures, of BASELINE configs 3 / 4 as bench.py and
+# tests/ draw it, and one more set
+CALIBRATION_AUDIO = [(2, 2.0, 1234, True), (8, 15.0, 77, False), (8, 10.0, 1234, False), (8, 10.0, 4321, False)]
 
-def main(model_name: str, target: float):
+
+def _rate(orc, enc, enc_len, sd, max_symbols):
+    with torch.inference_mode():
+        dec = orc.rnnt_greedy(enc, enc_len, sd, max_symbols)
+    return sum(len(d[0]) for d in dec) / float(enc_len.sum()), dec
+
+
+def calibrate(model_name: str, target: float) -> dict:
     from gigaam_b200 import synthetic
     from oracle import gigaam_oracle as orc
 
-    synthetic.RNNT_BLANK_BIAS[model_name] = 0.0
-    ck = synthetic.synthetic_checkpoint(model_name, seed=0)
+    ck = synthetic.synthetic_checkpoint(model_name, seed=0, rnnt_calibration={})     # gains only, no centring / bias
     cfg, sd = ck["cfg"], ck["state_dict"]
-    wav, wav_len = synthetic.synthetic_audio(4, 5.0, seed=1234, ragged=True)
-    with torch.inference_mode():
-        enc, enc_len = orc.model_forward(wav, wav_len, sd, cfg)
-    base = sd["head.joint.joint_net.1.bias"][-1].item()
-
-    def rate(bias: float) -> float:
-        sd["head.joint.joint_net.1.bias"][-1] = base + bias
+    ms = cfg["decoding"]["max_symbols_per_step"]
+    sets = []
+    for B, sec, seed, ragged in CALIBRATION_AUDIO:
+        wav, wav_len = synthetic.synthetic_audio(B, sec, seed=seed, ragged=ragged)
         with torch.inference_mode():
-            dec = orc.rnnt_greedy(enc, enc_len, sd, cfg["decoding"]["max_symbols_per_step"])
-        return sum(len(d[0]) for d in dec) / float(enc_len.sum())
+            sets.append(orc.model_forward(wav, wav_len, sd, cfg))
+    frames = torch.cat([e.transpose(1, 2)[torch.arange(e.shape[2])[None, :] < l[:, None]] for e, l in sets])
+    enc_mean = frames.mean(0)
+    sd["head.joint.enc.bias"] = -(sd["head.joint.enc.weight"] @ enc_mean)
+    base = sd["head.joint.joint_net.1.bias"][-1].item()
+    total = float(sum(int(l.sum()) for _, l in sets))
 
-    lo, hi = 0.0, 40.0
-    for _ in range(14):
+    def pooled(bias):
+        sd["head.joint.joint_net.1.bias"][-1] = base + bias
+        decs = [_rate(orc, e, l, sd, ms)[1] for e, l in sets]
+        return sum(len(d[0]) for dec in decs for d in dec) / total, decs
+
+    lo, hi = 0.0, 400.0
+    for _ in range(16):
         mid = 0.5 * (lo + hi)
-        r = rate(mid)
-        print(f"bias {mid:.4f} -> {r:.3f} tok/frame")
-        if r > target:
-            lo = mid
-        else:
-            hi = mid
-    print("calibrated bias ~", round(0.5 * (lo + hi), 3))
+        lo, hi = (mid, hi) if pooled(mid)[0] > target else (lo, mid)
+    bias = round(0.5 * (lo + hi), 3)
+    r, decs = pooled(bias)
+    print(f"{model_name}: blank bias {bias} -> {r:.3f} tokens/frame pooled (target {target})")
+    for (B, sec, seed, ragged), (e, l), dec in zip(CALIBRATION_AUDIO, sets, decs):
+        bursts = collections.Counter()
+        for d in dec:
+            bursts.update(collections.Counter(d[1]).values())
+        print(f"    {B} x {sec} s seed {seed}{' ragged' if ragged else ''}: {sum(len(d[0]) for d in dec) / float(l.sum()):.3f} tokens/frame, "
+              f"per utterance {[len(d[0]) for d in dec]}, tokens-per-emitting-frame {sorted(bursts.items())}")
+    for db in (-1.0, 1.0):
+        print(f"    bias {db:+.0f}: {pooled(bias + db)[0]:.3f} pooled")
+    return {"enc_mean": enc_mean.numpy().astype(np.float32), "blank_bias": np.float32(bias), "rate": np.float32(r)}
+
+
+def main(names):
+    from gigaam_b200 import synthetic
+    out = synthetic.RNNT_CALIBRATION_FILE
+    store = dict(np.load(out)) if out.exists() else {}
+    for name in names:
+        for k, v in calibrate(name, TARGETS[name]).items():
+            store[f"{name}/{k}"] = v
+    np.savez_compressed(out, **store)
+    print("wrote", out)
 
 
 if __name__ == "__main__":
-    main(sys.argv[1] if len(sys.argv) > 1 else "v2_rnnt", float(sys.argv[2]) if len(sys.argv) > 2 else 0.5)
+    torch.set_num_threads(8)
+    main(sys.argv[1:] or list(TARGETS))

@@ -67,8 +67,72 @@ def test_gemm_epilogues(eng_ctc, dev, M, N, K):
         assert rel(out.float(), want) < (1e-3 if kind < 3 else 1e-5), f"kind {kind}"
 
 
+def _rope_ref(u, T, cos, sin):
+    """apply_rotary_pos_emb of gigaam/utils.py:83-100 on [rows, 768] with t = row % T (16 heads x 48)."""
+    rows = u.shape[0]
+    x = u.view(rows, 16, 48)
+    t = torch.arange(rows, device=u.device) % T
+    c = torch.cat([cos[t], cos[t]], -1)[:, None, :]
+    s_ = torch.cat([sin[t], sin[t]], -1)[:, None, :]
+    rot = torch.cat([-x[..., 24:], x[..., :24]], -1)
+    return (x * c + rot * s_).reshape(rows, 768)
+
+
+@pytest.mark.parametrize("M,K,T", [(51, 768, 51), (1000, 768, 251), (777, 3072, 259), (16064, 768, 251), (300, 3072, 100)])
+def test_gemm_with_fused_layernorm_epilogue(eng_ctc, dev, M, K, T):
+    """EPI_BIAS_RES_LN_F32 (gemm_params.cuh: LnFuse): the residual GEMM followed by LayerNorm (mode 1), LayerNorm + rotary
+    embedding (mode 2) and norm_out + the next layer's first LayerNorm (mode 3), against torch fp32 on the same operands.
+    The row statistics cross CTA pairs through global memory; M = 16064 is the BASELINE config-2 row count (3 waves)."""
+    from gigaam_b200.engine import rotary_half_tables
+    g = torch.Generator().manual_seed(M + K)
+    A = (torch.randn(M, K, generator=g) * 0.5).half().to(dev)
+    W = (torch.randn(768, K, generator=g) / K ** 0.5).half().to(dev)
+    bias = torch.randn(768, generator=g).to(dev)
+    res = (torch.randn(M, 768, generator=g) * 2.0 + 0.3).to(dev)
+    g1, b1, g2, b2 = ((1.0 + 0.1 * torch.randn(768, generator=g)).to(dev), (0.05 * torch.randn(768, generator=g)).to(dev),
+                      (1.0 + 0.1 * torch.randn(768, generator=g)).to(dev), (0.05 * torch.randn(768, generator=g)).to(dev))
+    cos, sin = (t.to(dev) for t in rotary_half_tables(48, 5000.0, 5000))
+    x_want = res + 0.5 * (A.float() @ W.float().t() + bias)
+    ln1 = F.layer_norm(x_want, (768,), g1, b1, 1e-5)
+    ws = torch.empty(2 * ((M * 48 + 1023) // 1024 * 1024) + 2 * ((M + 255) // 256) * 32 + 1024, dtype=torch.uint8, device=dev)
+    for mode in (1, 2, 3, 30):
+        x = res.clone()
+        out16 = torch.zeros(M, 768, dtype=torch.float16, device=dev)
+        rope16 = torch.zeros(M, 768, dtype=torch.float16, device=dev)
+        last = mode == 30          # mode 3 without a second LayerNorm, result into a separate buffer (last layer -> enc)
+        xout = torch.zeros(M, 768, device=dev) if last else x
+        rc = eng_ctc.lib.gam_test_gemm_ln(eng_ctc.handle, 3 if last else mode, A.data_ptr(), W.data_ptr(), bias.data_ptr(), x.data_ptr(),
+                                          g1.data_ptr(), b1.data_ptr(), None if (last or mode != 3) else g2.data_ptr(),
+                                          None if (last or mode != 3) else b2.data_ptr(), out16.data_ptr(), rope16.data_ptr(),
+                                          xout.data_ptr(), M, K, T, 0.5, ws.data_ptr(), ws.numel(), _stream())
+        torch.cuda.synchronize()
+        assert rc == 0, mode
+        if mode in (1, 2):
+            assert rel(x, x_want) < 1e-5
+            assert rel(out16.float(), ln1) < 1e-3, mode
+        if mode == 2:
+            assert rel(rope16.float(), _rope_ref(ln1, T, cos, sin)) < 1e-3
+        if mode == 3:
+            assert rel(x, ln1) < 2e-5
+            assert rel(out16.float(), F.layer_norm(ln1, (768,), g2, b2, 1e-5)) < 1e-3
+        if last:
+            assert rel(x, x_want) < 1e-5 and rel(xout, ln1) < 2e-5
+    # deterministic: fixed slots, fixed summation order
+    outs = []
+    for _ in range(2):
+        x = res.clone()
+        out16 = torch.zeros(M, 768, dtype=torch.float16, device=dev)
+        rope16 = torch.zeros(M, 768, dtype=torch.float16, device=dev)
+        eng_ctc.lib.gam_test_gemm_ln(eng_ctc.handle, 2, A.data_ptr(), W.data_ptr(), bias.data_ptr(), x.data_ptr(), g1.data_ptr(),
+                                     b1.data_ptr(), None, None, out16.data_ptr(), rope16.data_ptr(), x.data_ptr(), M, K, T, 0.5,
+                                     ws.data_ptr(), ws.numel(), _stream())
+        torch.cuda.synchronize()
+        outs.append((x, out16, rope16))
+    assert all(torch.equal(a, b) for a, b in zip(*outs))
+
+
 @pytest.mark.parametrize("B,T,lens", [(1, 128, None), (2, 51, [51, 30]), (3, 251, [251, 200, 97]), (2, 376, [376, 129]),
-                                      (1, 626, None), (2, 5, [5, 1]), (2, 129, [129, 128])])
+                                      (1, 626, None), (2, 5, [5, 1]), (2, 129, [129, 128]), (2, 751, [751, 640]), (1, 768, None)])
 def test_attention_matches_masked_softmax(eng_ctc, dev, B, T, lens):
     g = torch.Generator().manual_seed(B * 1000 + T)
     d, H, dk = 768, 16, 48
@@ -100,13 +164,12 @@ def test_logmel_matches_oracle(eng_ctc, v2_ctc_ckpt, B, sec, ragged):
     assert float((got - want).abs().mean()) < 1e-4
 
 
-def test_logmel_fused_cuda_core_kernel_still_matches(eng_ctc, v2_ctc_ckpt, monkeypatch):
+def test_logmel_fused_cuda_core_kernel_still_matches(eng_ctc, v2_ctc_ckpt):
     """The single fused kernel (gam_logmel) and the tensor-core split-precision path (gam_logmel_tc) agree."""
     wav, _ = synthetic.synthetic_audio(2, 3.0, seed=13, ragged=True)
     want = orc.log_mel(wav, v2_ctc_ckpt["state_dict"], v2_ctc_ckpt["cfg"]["preprocessor"])
     tc = eng_ctc.logmel(wav.cuda()).cpu()
-    monkeypatch.setenv("GAM_LOGMEL_FUSED", "1")
-    fused = eng_ctc.logmel(wav.cuda()).cpu()
+    fused = eng_ctc.logmel(wav.cuda(), fused=True).cpu()
     for got in (tc, fused):
         assert float((got - want).abs().max()) < 5e-3 and float((got - want).abs().mean()) < 1e-4
     assert float((tc - fused).abs().max()) < 5e-3
@@ -152,8 +215,8 @@ def test_end_to_end_against_reference_golden(eng_ctc, golden_ctc):
 
 
 def test_ctc_ids_margin_aware_larger_batch(eng_ctc, v2_ctc_ckpt):
-    """Bit-exact CTC ids wherever the oracle's top-2 margin exceeds the activation noise; sub-margin frames are
-    counted and must be rare (SURVEY 7 'hard parts')."""
+    """Bit-exact CTC ids wherever the oracle's top-2 margin exceeds the FIXED margin CTC_MARGIN_EPS (derived from the
+    1e-3 activation budget, see the BASELINE-size tests below); sub-margin frames are counted (SURVEY 7 'hard parts')."""
     cfg, sd = v2_ctc_ckpt["cfg"], v2_ctc_ckpt["state_dict"]
     wav, wav_len = synthetic.synthetic_audio(4, 5.0, seed=99, ragged=True)
     with torch.inference_mode():
@@ -167,11 +230,10 @@ def test_ctc_ids_margin_aware_larger_batch(eng_ctc, v2_ctc_ckpt):
     top2 = logits.topk(2, dim=-1).values
     margin = top2[..., 0] - top2[..., 1]
     valid = torch.arange(logits.shape[1])[None, :] < len_o[:, None]
-    noise = 2.0 * float((F.conv1d(enc.cpu().transpose(1, 2), sd["head.decoder_layers.0.weight"]) .transpose(1, 2) -
-                         F.conv1d(enc_o, sd["head.decoder_layers.0.weight"]).transpose(1, 2))[valid].abs().max())
-    safe = valid & (margin > noise)
+    safe = valid & (margin > CTC_MARGIN_EPS)
+    print(f"CTC: {int((valid & ~safe).sum())} of {int(valid.sum())} frames below the {CTC_MARGIN_EPS} margin")
     assert torch.equal(lab_gpu[safe], logits.argmax(-1)[safe])
-    assert float((valid & ~safe).sum()) / float(valid.sum()) < 0.10
+    assert float((valid & ~safe).sum()) / float(valid.sum()) < CTC_SUBMARGIN_MAX
 
 
 def test_batch_vs_single_consistency(eng_ctc):
@@ -349,38 +411,130 @@ def test_fp16_encoder_weights_stay_within_tolerance(dev, v2_ctc_ckpt):
     assert rel(e16.transpose(1, 2)[valid], e32.transpose(1, 2)[valid]) < 3e-3
 
 
-# ------------------------------------------------------------------------------------------ BASELINE-size properties
-def test_config2_full_size_properties(dev, v2_ctc_ckpt):
-    """BASELINE.json configs[1] (v2_ctc, 64 x 10 s): shapes, finiteness, determinism, and equality of the first
-    utterances with a small-batch run of the same audio (utterances are independent)."""
-    model = gigaam.load_model("v2_ctc", fp16_encoder=False, device=dev, checkpoint=v2_ctc_ckpt)
-    wav, wav_len = synthetic.synthetic_audio(64, 10.0, seed=1234)
+# ------------------------------------------------------------------------------------------ BASELINE sizes, benchmarked mode
+# Every BASELINE.json config at its stated per-GPU size, through load_model(...) with the DEFAULT fp16_encoder=True (the
+# mode bench.py times), against the oracle run on the same fp16-rounded-then-float encoder parameters
+# (gigaam/__init__.py:188-189: `model.encoder.half()` rounds every encoder tensor, the head stays fp32).
+# Fixed logit margin, derived once from the activation budget: a relative error of 1e-3 on a frame of norm ~27.7 moves a
+# logit (head-row norm ~2.3) by 2.3 * 0.0277 / sqrt(768) = 2.3e-3 rms and a top-2 difference by 3.3e-3 rms -> 3 sigma.
+CTC_MARGIN_EPS = 0.01
+# The synthetic head on the stationary test signal has many near-ties: 3.6 % of config 2's frames (oracle alone, CPU
+# measurement) sit below the margin; they are counted and reported, not compared.
+CTC_SUBMARGIN_MAX = 0.06
+
+
+def _fp16_rounded(sd):
+    return {k: (v.half().float() if k.startswith("encoder.") and v.is_floating_point() else v) for k, v in sd.items()}
+
+
+def _encoder_parity(model, ckpt, wav, wav_len, dev):
+    sd16 = _fp16_rounded(ckpt["state_dict"])
     enc, enc_len = model(wav.to(dev), wav_len.to(dev))
-    assert enc.shape == (64, 768, 251) and bool((enc_len == 251).all()) and torch.isfinite(enc).all()
-    ids, frames, counts = model.decoding.decode_device(model.head, enc, enc_len)
+    with torch.inference_mode():
+        enc_o, len_o = orc.model_forward(wav, wav_len, sd16, ckpt["cfg"])
+    assert torch.equal(enc_len.cpu(), len_o)
+    assert torch.isfinite(enc).all()
+    got, want = enc.cpu().transpose(1, 2), enc_o.transpose(1, 2)
+    valid = torch.arange(want.shape[1])[None, :] < len_o[:, None]
+    r_all = rel(got[valid], want[valid])
+    r_utt = max(rel(got[i, : int(len_o[i])], want[i, : int(len_o[i])]) for i in range(wav.shape[0]))
+    print(f"encoder rel: all {r_all:.3e}, worst utterance {r_utt:.3e}")
+    assert r_all < ENC_REL_TOL and r_utt < 1.5 * ENC_REL_TOL
+    return enc, enc_len, enc_o, len_o, sd16
+
+
+def test_config2_full_size_against_oracle(dev, v2_ctc_ckpt):
+    """BASELINE.json configs[1]: v2_ctc, 64 x 10 s (R = 16 064 rows: three GEMM waves, the benchmarked shape)."""
+    model = gigaam.load_model("v2_ctc", device=dev, checkpoint=v2_ctc_ckpt)
+    assert model._dtype == torch.float16
+    wav, wav_len = synthetic.synthetic_audio(64, 10.0, seed=1234)
+    enc, enc_len, enc_o, len_o, sd16 = _encoder_parity(model, v2_ctc_ckpt, wav, wav_len, dev)
+    assert enc.shape == (64, 768, 251)
+    # CTC ids: frame labels from the GPU activations == oracle labels wherever the oracle margin exceeds the FIXED eps
+    logits = orc.ctc_logits(enc_o, sd16)
+    top2 = logits.topk(2, dim=-1).values
+    margin = top2[..., 0] - top2[..., 1]
+    lab_gpu = F.conv1d(enc.cpu(), sd16["head.decoder_layers.0.weight"], sd16["head.decoder_layers.0.bias"]).argmax(1)
+    valid = torch.arange(logits.shape[1])[None, :] < len_o[:, None]
+    safe = valid & (margin > CTC_MARGIN_EPS)
+    n_sub = int((valid & ~safe).sum())
+    print(f"CTC: {n_sub} of {int(valid.sum())} frames below the {CTC_MARGIN_EPS} margin; "
+          f"{int((lab_gpu != logits.argmax(-1))[valid].sum())} label differences in total")
+    assert torch.equal(lab_gpu[safe], logits.argmax(-1)[safe])
+    assert n_sub / float(valid.sum()) < CTC_SUBMARGIN_MAX
+    # the device decoder on its own activations == the oracle decoder on the same activations (bit exact away from fp32 ties)
+    ids, frames, counts = (t.cpu() for t in model.decoding.decode_device(model.head, enc, enc_len))
+    want = orc.ctc_greedy(enc.cpu(), enc_len.cpu(), sd16)
+    lg = orc.ctc_logits(enc.cpu(), sd16).topk(2, dim=-1).values
+    tie_free = ((lg[..., 0] - lg[..., 1]) > 1e-4).all(1)
+    assert int(tie_free.sum()) >= 60
+    for b in range(64):
+        n = int(counts[b])
+        if tie_free[b]:
+            assert ids[b, :n].tolist() == want[b][0] and frames[b, :n].tolist() == want[b][1], b
+    # determinism and batch independence at this size
     enc2, _ = model(wav.to(dev), wav_len.to(dev))
     assert torch.equal(enc, enc2)
-    enc_s, len_s = model(wav[:2].to(dev), wav_len[:2].to(dev))
+    enc_s, _ = model(wav[:2].to(dev), wav_len[:2].to(dev))
     assert rel(enc_s, enc[:2]) < 1e-6 or float((enc_s - enc[:2]).abs().max()) < 1e-3
-    ids_s, frames_s, counts_s = model.decoding.decode_device(model.head, enc[:2].contiguous(), enc_len[:2])
-    for b in range(2):
+
+
+def _rnnt_on_oracle_activations(model, enc_o, len_o, sd, max_symbols, dev):
+    ids, frames, counts = (t.cpu() for t in model.decoding.decode_device(model.head, enc_o.to(dev), len_o.to(dev)))
+    want = orc.rnnt_greedy(enc_o, len_o, sd, max_symbols)
+    total = 0
+    for b in range(enc_o.shape[0]):
         n = int(counts[b])
-        assert n == int(counts_s[b]) and torch.equal(ids[b, :n], ids_s[b, :n]) and torch.equal(frames[b, :n], frames_s[b, :n])
-        assert bool((frames[b, :n] < 251).all()) and bool((ids[b, :n] < 33).all())
+        total += n
+        assert ids[b, :n].tolist() == want[b][0] and frames[b, :n].tolist() == want[b][1], b
+    rate = total / float(len_o.sum())
+    print(f"RNN-T: {total} tokens, {rate:.3f} tokens/frame")
+    return rate
 
 
-def test_config3_rnnt_full_size_runs(dev, v2_rnnt_ckpt):
-    """BASELINE.json configs[2] (v2_rnnt, 32 x 15 s): device-resident RNN-T loop; spot-check utterance 0 against the
-    oracle decode of the SAME encoder activations (exact ids)."""
-    model = gigaam.load_model("v2_rnnt", fp16_encoder=False, device=dev, checkpoint=v2_rnnt_ckpt)
+def test_config3_full_size_against_oracle(dev, v2_rnnt_ckpt):
+    """BASELINE.json configs[2]: v2_rnnt, 32 x 15 s.  Encoder vs oracle; the device RNN-T loop fed the ORACLE's activations
+    must reproduce the oracle's hypotheses for all 32 utterances."""
+    model = gigaam.load_model("v2_rnnt", device=dev, checkpoint=v2_rnnt_ckpt)
     wav, wav_len = synthetic.synthetic_audio(32, 15.0, seed=77)
-    enc, enc_len = model(wav.to(dev), wav_len.to(dev))
+    enc, enc_len, enc_o, len_o, sd16 = _encoder_parity(model, v2_rnnt_ckpt, wav, wav_len, dev)
     assert enc.shape == (32, 768, 376)
+    rate = _rnnt_on_oracle_activations(model, enc_o, len_o, sd16, 10, dev)
+    assert 0.1 < rate < 2.0          # calibrated head (oracle/calibrate_rnnt.py), target 0.5
     ids, frames, counts = model.decoding.decode_device(model.head, enc, enc_len)
-    want = orc.rnnt_greedy(enc[:1].cpu(), enc_len[:1].cpu(), v2_rnnt_ckpt["state_dict"], 10)
-    n = int(counts[0])
-    assert n > 0 and ids[0, :n].tolist() == want[0][0] and frames[0, :n].tolist() == want[0][1]
-    assert bool((counts <= 376 * 10).all())
+    assert bool((counts <= 376 * 10).all()) and int(counts.sum()) > 0
+
+
+def test_config4_per_gpu_size_against_oracle(dev, v3_ckpt):
+    """BASELINE.json configs[3]: v3_e2e_rnnt 256 x 10 s over 8 GPUs = 32 x 10 s per GPU (conv1d subsampling, LayerNorm conv
+    module, 1025 classes: part of W_o streams from L2 in the RNN-T kernel)."""
+    model = gigaam.load_model("v3_e2e_rnnt", device=dev, checkpoint=v3_ckpt)
+    wav, wav_len = synthetic.synthetic_audio(32, 10.0, seed=1234)
+    enc, enc_len, enc_o, len_o, sd16 = _encoder_parity(model, v3_ckpt, wav, wav_len, dev)
+    assert enc.shape == (32, 768, 250)
+    rate = _rnnt_on_oracle_activations(model, enc_o, len_o, sd16, 10, dev)
+    assert 0.03 < rate < 1.0         # target 0.2
+
+
+def test_config5_slice_against_oracle(dev):
+    """BASELINE.json configs[4]: v2_ssl embed path, 25 s utterances (T' = 626, the long attention kernel, s1 of
+    0.5 G elements per 16 utterances); a 16-utterance slice of the 128 x 25 s batch."""
+    ck = synthetic.synthetic_checkpoint("v2_ssl", seed=0)
+    model = gigaam.load_model("v2_ssl", device=dev, checkpoint=ck)
+    wav, wav_len = synthetic.synthetic_audio(16, 25.0, seed=1234)
+    enc, enc_len, _, _, _ = _encoder_parity(model, ck, wav, wav_len, dev)
+    assert enc.shape == (16, 768, 626)
+
+
+def test_segment_of_30s_runs_and_matches_oracle(dev, v2_ctc_ckpt):
+    """The reference's VAD emits segments of up to 30 s (gigaam/vad_utils.py:85,105-118) and forward() has no length
+    guard: T' = 751 (six key blocks)."""
+    model = gigaam.load_model("v2_ctc", device=dev, checkpoint=v2_ctc_ckpt)
+    wav, wav_len = synthetic.synthetic_audio(2, 30.0, seed=31, ragged=True)
+    enc, enc_len, _, _, _ = _encoder_parity(model, v2_ctc_ckpt, wav, wav_len, dev)
+    assert enc.shape[2] == 751
+    with pytest.raises(Exception, match="limit"):
+        model(torch.zeros(1, 31 * 16000, device=dev), torch.tensor([31 * 16000], device=dev))
 
 
 # ------------------------------------------------------------------------------------------ v3 shape (conv1d / LN conv-norm / k5 / n_fft 320)
@@ -434,7 +588,8 @@ def eng_v1(dev, v1_ctc_ckpt):
 
 
 @pytest.mark.parametrize("B,T,lens", [(1, 128, None), (2, 51, [51, 30]), (3, 251, [251, 200, 97]), (2, 376, [376, 129]),
-                                      (1, 626, None), (2, 5, [5, 1]), (2, 129, [129, 128]), (3, 300, [300, 0, 257]), (1, 640, None)])
+                                      (1, 626, None), (2, 5, [5, 1]), (2, 129, [129, 128]), (3, 300, [300, 0, 257]), (1, 640, None),
+                                      (2, 751, [751, 700])])
 def test_relpos_attention_matches_shifted_softmax(eng_v1, dev, B, T, lens):
     """gam_test_attention_relpos vs the reference formula (gigaam/encoder.py:216-228) in torch fp32, with the
     reference's own pad/view rel_shift, on the same fp16 operands."""
@@ -535,6 +690,42 @@ def test_batch_pipeline_equals_direct_calls(dev, v2_ctc_ckpt, use_graph):
     for g, w in zip(got, want):
         assert g == w
     assert sum(len(h[1]) for hyps in want for h in hyps) > 0
+
+
+def test_batch_pipeline_many_shapes_keeps_graph_workspaces_alive(dev, v2_ctc_ckpt):
+    """More input shapes than the engine's workspace cache holds (4 per kind), revisited in a round robin: every cached
+    graph keeps writing into scratch memory it owns, so replays after the engine has forgotten the shape still give the
+    plain-call results, and device memory stays bounded."""
+    from gigaam_b200.pipeline import BatchPipeline
+    model = gigaam.load_model("v2_ctc", device=dev, checkpoint=v2_ctc_ckpt)
+    shapes = [(2, 1.0), (2, 1.5), (3, 1.0), (1, 2.0), (2, 2.5), (3, 0.8)]
+    batches = []
+    for rnd in range(3):
+        for i, (B, sec) in enumerate(shapes):
+            wav, wav_len = synthetic.synthetic_audio(B, sec, seed=300 + 10 * rnd + i, ragged=True)
+            batches.append((wav.pin_memory(), wav_len))
+    want = []
+    for wav, wav_len in batches:
+        enc, enc_len = model(wav.to(dev), wav_len.to(dev))
+        want.append(model.decoding.decode(model.head, enc, enc_len))
+    pipe = BatchPipeline(model, use_graph=True, max_graphs=len(shapes))
+    got = list(pipe.run(iter(batches)))
+    assert got == want
+    eng = model._get_engine()
+    assert len(eng._ws_enc) <= eng.WS_CACHE and len(eng._ws_mel) <= eng.WS_CACHE and len(eng._ws_dec) <= eng.WS_CACHE
+
+
+def test_many_distinct_lengths_do_not_leak_workspaces(dev, v2_ctc_ckpt):
+    """transcribe() over many different lengths (what eval / long-form loops do): the engine's scratch caches are bounded
+    per kind, so allocated device memory levels off instead of growing with the number of shapes seen."""
+    model = gigaam.load_model("v2_ctc", device=dev, checkpoint=synthetic.synthetic_checkpoint("v2_ctc", seed=0, n_layers=2))
+    wav, _ = synthetic.synthetic_audio(1, 6.0, seed=5)
+    peaks = []
+    for i in range(24):
+        model.transcribe(wav[0, : 16000 + 3217 * ((7 * i) % 24)])      # 24 distinct lengths, shuffled
+        torch.cuda.synchronize()
+        peaks.append(torch.cuda.memory_allocated(dev))
+    assert max(peaks[12:]) <= max(peaks[:12]) * 1.5 + (64 << 20)
 
 
 def test_transcribe_longform_equals_per_segment_transcribe(dev, v2_ctc_ckpt):
