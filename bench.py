@@ -4,7 +4,7 @@
     python bench.py --gpus 1 --steps 20 --warmup 3
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
-    python bench.py --impl reference --steps 2 --warmup 1       # the reference's CPU path (oracle port) on host cores
+    python bench.py --impl reference --steps 2 --warmup 1       # the unmodified reference (oracle/_ref archive) on host cores
 
 Workload (BASELINE.json configs[1]): v2_ctc, batch 64 x 10 s synthetic 16 kHz audio per GPU (weak scaling:
 every rank runs its own 64 utterances, hypotheses all-gathered to every rank over NCCL when N > 1), seeded
@@ -13,8 +13,8 @@ random weights of the reference's shape (no checkpoints offline).
 One JSON line on stdout (rank 0): see the task contract.  `value` = device-resident throughput (CUDA graph of
 the whole step, rotating input buffers larger than L2), `e2e` = the same metric through the public API
 (`model.forward` + `model.decoding.decode`) from pinned HOST buffers with the H2D / D2H copies inside the timed
-region, `roofline` = the dominant kernel class timed live with CUDA events, `cpu_baseline` = the oracle port of the
-reference's CPU path on the box's host cores.
+region, `roofline` = the dominant kernel class timed live with CUDA events, `cpu_baseline` = the unmodified reference (oracle/_ref, else the oracle port) on the
+box's host cores.
 """
 from __future__ import annotations
 
@@ -102,16 +102,37 @@ class ClockSampler:
 
 
 def cpu_reference(steps: int, warmup: int, batch: int = 4, reps: int = 3, seconds: float = SECONDS):
-    """The reference's CPU PyTorch path restated (oracle/gigaam_oracle.py: same ATen ops, fp32, no autocast --
-    gigaam/model.py:34-35) on all host cores: log-mel + encoder + CTC greedy incl. host detokenisation."""
+    """The reference's own CPU PyTorch path on all host cores: log-mel + encoder + CTC greedy incl. host detokenisation,
+    fp32, no autocast (gigaam/model.py:34-35).  Runs the UNMODIFIED reference modules byte-compiled into
+    oracle/_ref/gigaam_ref.zip (oracle/build_ref.py; kind "reference"); only if that archive is missing does it time the
+    oracle port of the same ATen ops (oracle/gigaam_oracle.py; kind "port")."""
     import torch
     from gigaam_b200 import synthetic
-    from oracle import gigaam_oracle as orc
 
     ck = synthetic.synthetic_checkpoint(MODEL, seed=0)
     cfg, sd = ck["cfg"], ck["state_dict"]
     wav, wav_len = synthetic.synthetic_audio(batch, seconds, seed=1234)
     vocab = cfg["decoding"]["vocabulary"]
+    try:
+        from oracle.ref_loader import build_reference
+        ref_root, ref_decoding = build_reference(cfg, sd)
+        kind = "reference"
+
+        def forward(w, l):
+            mel, mel_len = ref_root.preprocessor(w, l)
+            return ref_root.encoder(mel, mel_len)
+
+        def decode(enc, enc_len):
+            return [t for t, _, _ in ref_decoding.decode(ref_root.head, enc, enc_len)]
+    except ImportError:
+        from oracle import gigaam_oracle as orc
+        kind = "port"
+
+        def forward(w, l):
+            return orc.model_forward(w, l, sd, cfg)
+
+        def decode(enc, enc_len):
+            return ["".join(vocab[i] for i in ids) for ids, _ in orc.ctc_greedy(enc, enc_len, sd)]
     # all host threads the process may use: affinity mask capped by the cgroup CPU quota (a 128-thread pool on a
     # quota of a few CPUs thrashes); then keep the fastest of {all, 1/2, 1/4} on a short probe
     avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
@@ -126,9 +147,9 @@ def cpu_reference(steps: int, warmup: int, batch: int = 4, reps: int = 3, second
     for n in sorted({avail, max(1, avail // 2), max(1, avail // 4)}, reverse=True):
         torch.set_num_threads(n)
         with torch.inference_mode():
-            orc.model_forward(probe_wav, probe_len, sd, cfg)
+            forward(probe_wav, probe_len)
             t0 = time.perf_counter()
-            orc.model_forward(probe_wav, probe_len, sd, cfg)
+            forward(probe_wav, probe_len)
             dt = time.perf_counter() - t0
         if best is None or dt < best:
             best, cores = dt, n
@@ -140,9 +161,8 @@ def cpu_reference(steps: int, warmup: int, batch: int = 4, reps: int = 3, second
         out = []
         for _ in range(reps):
             with torch.inference_mode():
-                enc, enc_len = orc.model_forward(wav, wav_len, sd, cfg)
-                hyp = orc.ctc_greedy(enc, enc_len, sd)
-            out += ["".join(vocab[i] for i in ids) for ids, _ in hyp]
+                enc, enc_len = forward(wav, wav_len)
+                out += decode(enc, enc_len)
         return out
 
     for _ in range(warmup):
@@ -153,7 +173,7 @@ def cpu_reference(steps: int, warmup: int, batch: int = 4, reps: int = 3, second
         step()
         times.append(time.perf_counter() - t0)
     sec = statistics.median(times)
-    return {"value": batch * reps / sec, "unit": "utt/s", "cores": cores, "kind": "port",
+    return {"value": batch * reps / sec, "unit": "utt/s", "cores": cores, "kind": kind,
             "sample": f"{reps} batches of {batch} x {seconds:g} s utterances of the same workload per step, median of {steps} steps "
                       f"after {warmup} warm-up, torch {torch.__version__} fp32, {cores} threads",
             "rtfx": batch * reps * seconds / sec, "sec_per_step": sec}

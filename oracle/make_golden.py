@@ -12,7 +12,6 @@ from __future__ import annotations
 
 import os
 import sys
-import types
 from pathlib import Path
 
 import numpy as np
@@ -20,47 +19,9 @@ import torch
 
 ROOT = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT))
-REF = os.environ.get("GIGAAM_REFERENCE", "/root/reference")
 
 
-def import_reference():
-    for name in ("hydra", "hydra.utils", "omegaconf", "soundfile"):
-        if name not in sys.modules:
-            sys.modules[name] = types.ModuleType(name)
-    sys.modules["hydra"].utils = sys.modules["hydra.utils"]
-    sys.modules["omegaconf"].DictConfig = dict
-    sys.modules["omegaconf"].ListConfig = list
-    if REF not in sys.path:
-        sys.path.insert(0, REF)
-    import gigaam.decoder as ref_decoder
-    import gigaam.decoding as ref_decoding
-    import gigaam.encoder as ref_encoder
-    import gigaam.preprocess as ref_preprocess
-    return ref_preprocess, ref_encoder, ref_decoder, ref_decoding
-
-
-def build_reference(cfg, sd):
-    """Instantiate the reference modules for a plain-dict cfg and load the seeded state_dict (strict)."""
-    rp, re_, rd, rdec = import_reference()
-    pre_kw = {k: v for k, v in cfg["preprocessor"].items()}
-    pre = rp.FeatureExtractor(**pre_kw)
-    enc = re_.ConformerEncoder(**cfg["encoder"])
-    mods = {"preprocessor": pre, "encoder": enc}
-    head = cfg.get("head")
-    decoding = None
-    if head is not None:
-        if head["type"] == "ctc":
-            mods["head"] = rd.CTCHead(head["feat_in"], head["num_classes"])
-            decoding = rdec.CTCGreedyDecoding(cfg["decoding"]["vocabulary"])
-        else:
-            mods["head"] = rd.RNNTHead(head["decoder"], head["joint"])
-            decoding = rdec.RNNTGreedyDecoding(cfg["decoding"]["vocabulary"], None, cfg["decoding"]["max_symbols_per_step"])
-    root = torch.nn.Module()
-    for k, m in mods.items():
-        root.add_module(k, m)
-    missing, unexpected = root.load_state_dict(sd, strict=True), None
-    root.eval()
-    return root, decoding
+from oracle.ref_loader import build_reference  # noqa: E402
 
 
 def run_case(model_name: str, batch: int, seconds: float, ragged: bool, out_name: str, seed: int = 0):

@@ -314,10 +314,12 @@ def test_rnnt_blank_then_emit_patterns(eng_rnnt, v2_rnnt_ckpt):
     (the synthetic audio never produces this: its encoder output is almost constant in time).  Random, time-varying
     activations give hypotheses whose frame lists have gaps of both parities; ids and frames must still be exact."""
     sd = v2_rnnt_ckpt["state_dict"]
+    # the calibrated joint network cancels the mean encoder frame (oracle/calibrate_rnnt.py): frames = that mean + noise
+    mean = torch.as_tensor(synthetic._rnnt_calibration("v2_rnnt")["enc_mean"])
     gaps_seen = set()
-    for seed, scale in [(8, 0.5), (9, 0.5), (10, 0.4), (11, 0.6)]:
+    for seed, scale in [(8, 0.3), (9, 0.3), (10, 0.25), (11, 0.35)]:
         g = torch.Generator().manual_seed(seed)
-        enc = torch.randn(6, 40, 768, generator=g) * scale
+        enc = mean + torch.randn(6, 40, 768, generator=g) * scale
         enc_len = torch.tensor([40, 33, 0, 17, 40, 9], dtype=torch.int32)
         want = orc.rnnt_greedy(enc.transpose(1, 2), enc_len, sd, 10)
         ids, frames, counts = eng_rnnt.greedy(enc.cuda(), enc_len.cuda())
@@ -332,7 +334,7 @@ def test_rnnt_blank_then_emit_patterns(eng_rnnt, v2_rnnt_ckpt):
 
 def test_rnnt_edge_lengths(eng_rnnt, v2_rnnt_ckpt):
     g = torch.Generator().manual_seed(8)
-    enc = torch.randn(3, 20, 768, generator=g)
+    enc = torch.as_tensor(synthetic._rnnt_calibration("v2_rnnt")["enc_mean"]) + 0.3 * torch.randn(3, 20, 768, generator=g)
     enc_len = torch.tensor([20, 0, 1], dtype=torch.int32)
     want = orc.rnnt_greedy(enc.transpose(1, 2), enc_len, v2_rnnt_ckpt["state_dict"], 10)
     ids, frames, counts = eng_rnnt.greedy(enc.cuda(), enc_len.cuda())
@@ -354,7 +356,8 @@ def test_rnnt_large_batches_against_oracle_and_small_groups(which, B, eng_rnnt, 
         eng, sd = request.getfixturevalue("eng_v3"), request.getfixturevalue("v3_ckpt")["state_dict"]
     g = torch.Generator().manual_seed(21)
     T = 24
-    enc = torch.randn(B, T, 768, generator=g) * 0.5
+    mean = torch.as_tensor(synthetic._rnnt_calibration("v2_rnnt" if which == "v2" else "v3_e2e_rnnt")["enc_mean"])
+    enc = mean + torch.randn(B, T, 768, generator=g) * 0.3      # blank runs, single tokens and max_symbols bursts
     enc_len = torch.randint(0, T + 1, (B,), generator=g, dtype=torch.int32)
     enc_len[0], enc_len[7] = T, 0
     ids, frames, counts = (x.cpu() for x in eng.greedy(enc.cuda(), enc_len.cuda()))

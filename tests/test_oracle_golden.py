@@ -106,3 +106,33 @@ def test_ctc_collapse_edge_cases(v2_ctc_ckpt):
     assert got[2] == ([], [])
     got = orc.ctc_greedy(enc, torch.tensor([1, 1, 3]), sd)
     assert got[0] == ([3], [0]) and got[2] == ([1, 2, 3], [0, 1, 2])
+
+
+def test_compiled_reference_archive_reproduces_the_golden_vectors(golden_dir, v2_ctc_ckpt, monkeypatch):
+    """oracle/_ref/gigaam_ref.zip (oracle/build_ref.py: the reference's own modules, byte-compiled; what `bench.py --impl
+    reference` times on the GPU box) imported on its own -- not from /root/reference -- gives bit-identical log-mel,
+    encoder output and hypotheses to the committed fixtures.  Skipped only where the archive has not been built."""
+    from oracle import ref_loader
+    if not ref_loader.ARCHIVE.is_file():
+        pytest.skip("oracle/_ref/gigaam_ref.zip not built (oracle/build_ref.py needs /root/reference)")
+    import subprocess
+    import sys
+    code = (
+        "import sys, numpy as np, torch\n"
+        f"sys.path.insert(0, {str(ref_loader.ROOT)!r})\n"
+        "from oracle.ref_loader import build_reference, reference_root\n"
+        "from gigaam_b200 import synthetic\n"
+        "assert reference_root().endswith('gigaam_ref.zip')\n"
+        f"g = np.load({str(golden_dir / 'v2_ctc_b2_2s.npz')!r})\n"
+        "ck = synthetic.synthetic_checkpoint('v2_ctc', seed=0)\n"
+        "root, dec = build_reference(ck['cfg'], ck['state_dict'])\n"
+        "wav, wl = synthetic.synthetic_audio(2, 2.0, seed=1234, ragged=True)\n"
+        "with torch.inference_mode():\n"
+        "    mel, ml = root.preprocessor(wav, wl); enc, el = root.encoder(mel, ml); hyp = dec.decode(root.head, enc, el)\n"
+        "assert float((mel - torch.from_numpy(g['mel'])).abs().max()) == 0.0\n"
+        "assert float((enc - torch.from_numpy(g['enc'])).abs().max()) == 0.0\n"
+        "assert all(list(h[1]) == g[f'ids_{b}'].tolist() and list(h[2]) == g[f'frames_{b}'].tolist() for b, h in enumerate(hyp))\n"
+        "print('archive ok')\n")
+    env = dict(**__import__("os").environ, GIGAAM_REFERENCE_ARCHIVE_ONLY="1")
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
+    assert res.returncode == 0 and "archive ok" in res.stdout, res.stderr[-2000:]
