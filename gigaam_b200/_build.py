@@ -17,7 +17,7 @@ CSRC = PKG_DIR / "csrc"
 BUILD_DIR = PKG_DIR / "build"
 LIB_PATH = PKG_DIR / "libgigaam_b200.so"
 
-SOURCES = ["gam_api.cu", "gemm.cu", "attention_sm100.cu", "attention_relpos_sm100.cu", "rowops.cu", "frontend.cu", "ctc.cu", "rnnt.cu", "rnnt_cluster.cu"]
+SOURCES = ["gam_api.cu", "gemm.cu", "attention_sm100.cu", "attention_relpos_sm100.cu", "rowops.cu", "frontend.cu", "ctc.cu", "words.cu", "comm.cu", "rnnt.cu", "rnnt_cluster.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -66,7 +66,7 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
 
     with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    cmd = [nvcc, "-shared", "-o", str(LIB_PATH), *objs, "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a"]
+    cmd = [nvcc, "-shared", "-o", str(LIB_PATH), *objs, "-cudart", "static", "-ldl", "-gencode", "arch=compute_100a,code=sm_100a"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")

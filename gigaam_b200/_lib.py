@@ -51,7 +51,8 @@ EXPORTS = ("gam_create", "gam_destroy", "gam_last_error", "gam_version", "gam_lo
            "gam_workspace_bytes", "gam_logmel", "gam_encode", "gam_ctc_greedy", "gam_rnnt_greedy", "gam_test_gemm",
            "gam_test_attention", "gam_launch_count", "gam_profile_begin", "gam_profile_end", "gam_profile_class_count",
            "gam_profile_class_name", "gam_logmel_workspace_bytes", "gam_logmel_tc", "gam_test_attention_relpos",
-           "gam_decode_workspace_bytes", "gam_test_gemm_ln")
+           "gam_decode_workspace_bytes", "gam_test_gemm_ln", "gam_group_words", "gam_comm_unique_id", "gam_comm_init",
+           "gam_comm_nccl_version", "gam_gather_hyps")
 
 
 def lib_path() -> Path:
@@ -89,6 +90,15 @@ def load() -> C.CDLL:
     lib.gam_decode_workspace_bytes.restype = i64
     lib.gam_test_gemm_ln.argtypes = [H, i32] + [c_vp] * 11 + [i32, i32, i32, C.c_float, c_vp, i64, c_vp]
     lib.gam_test_gemm_ln.restype = C.c_int
+    lib.gam_comm_unique_id.argtypes = [c_vp]
+    lib.gam_comm_unique_id.restype = C.c_int
+    lib.gam_comm_init.argtypes = [H, c_vp, i32, i32]
+    lib.gam_comm_init.restype = C.c_int
+    lib.gam_comm_nccl_version.restype = i32
+    lib.gam_gather_hyps.argtypes = [H, c_vp, i64, c_vp, c_vp]
+    lib.gam_gather_hyps.restype = C.c_int
+    lib.gam_group_words.argtypes = [H, c_vp, c_vp, c_vp, i32, i32, c_vp, i32, i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]
+    lib.gam_group_words.restype = C.c_int
     lib.gam_logmel.argtypes = [H, c_vp, i32, i64, c_vp, c_vp]
     lib.gam_logmel.restype = C.c_int
     lib.gam_encode.argtypes = [H, c_vp, c_vp, i32, i64, c_vp, i64, c_vp, c_vp, i32, c_vp]

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "../../include/gigaam_b200.h"
+#include "comm.h"
 #include "gemm_params.cuh"
 #include "kernels.h"
 #include "launch.cuh"
@@ -120,6 +121,8 @@ struct gam_handle {
   int device = 0;
   int num_sms = 148;
   int64_t launches = 0;
+  void* comm = nullptr;      // ncclComm_t of gam_comm_init
+  int comm_rank = 0, comm_nranks = 1;
   std::string err;
   std::vector<Plan*> plans;
   // optional per-launch CUDA-event timing (bench.py's roofline leg); never active during graph capture
@@ -357,6 +360,7 @@ int gam_create(const gam_config* cfg, const gam_weights* w, int device, gam_hand
 void gam_destroy(gam_handle* h) {
   if (!h) return;
   for (Plan* p : h->plans) delete p;
+  comm_destroy(h->comm);
   delete h;
 }
 
@@ -627,6 +631,44 @@ int gam_rnnt_greedy(gam_handle* h, const float* enc, const int32_t* enc_len, int
   return 0;
 }
 
+int gam_group_words(gam_handle* h, const int32_t* ids, const int32_t* frames, const int32_t* counts, int32_t B, int32_t max_out,
+                    const uint8_t* token_flags, int32_t V, int32_t max_words, int32_t* word_start, int32_t* word_end,
+                    int32_t* word_first_token, int32_t* word_tokens, int32_t* n_words, void* stream) {
+  if (B < 0 || max_out <= 0 || max_words <= 0 || V <= 0) return fail(h, -1, "group_words: bad sizes");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  { PROF(PC_MISC);
+    launch_group_words(ids, frames, counts, token_flags, B, V, max_out, max_words, word_start, word_end, word_first_token, word_tokens,
+                       n_words, s); }
+  GAM_CHECK_LAUNCH(h, "group_words");
+  return 0;
+}
+
+int gam_comm_unique_id(uint8_t* out128) { return comm_unique_id(out128); }
+
+int gam_comm_init(gam_handle* h, const uint8_t* id128, int32_t rank, int32_t nranks) {
+  if (nranks < 1 || rank < 0 || rank >= nranks) return fail(h, -1, "comm_init: bad rank %d of %d", rank, nranks);
+  if (h->comm) { comm_destroy(h->comm); h->comm = nullptr; }
+  if (cudaSetDevice(h->device) != cudaSuccess) return fail(h, -11, "cudaSetDevice(%d) failed", h->device);
+  const char* err = "";
+  const int rc = comm_init(&h->comm, id128, rank, nranks, &err);
+  if (rc != 0) return fail(h, -20, "NCCL communicator init failed (rank %d of %d): %s", rank, nranks, err);
+  h->comm_rank = rank;
+  h->comm_nranks = nranks;
+  return 0;
+}
+
+int32_t gam_comm_nccl_version(void) { return comm_nccl_version(); }
+
+int gam_gather_hyps(gam_handle* h, const int32_t* packed, int64_t n_int32, int32_t* gathered, void* stream) {
+  if (!h->comm) return fail(h, -20, "gather_hyps: no communicator (call gam_comm_init first)");
+  if (n_int32 <= 0) return fail(h, -1, "gather_hyps: empty payload");
+  const char* err = "";
+  { cudaStream_t s = static_cast<cudaStream_t>(stream);
+    PROF(PC_MISC);
+    if (comm_all_gather_i32(h->comm, packed, gathered, n_int32, s, &err) != 0) return fail(h, -20, "ncclAllGather failed: %s", err); }
+  return 0;
+}
+
 int gam_profile_begin(gam_handle* h) {
   for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
   h->prof_ev.clear();
@@ -692,7 +734,8 @@ int gam_test_gemm_ln(gam_handle* h, int32_t mode, const void* A, const void* W, 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   LnFuse f{};
-  f.mode = mode;
+  f.mode = mode & 15;
+  f.dbg = mode >> 4;      // probes (tools/ln_probe.py); results are then undefined
   f.g = g; f.b = b; f.g2 = g2; f.b2 = b2;
   f.out16 = static_cast<__half*>(out16);
   f.rope16 = static_cast<__half*>(rope16);

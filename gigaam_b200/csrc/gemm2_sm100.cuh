@@ -132,7 +132,8 @@ __device__ __noinline__ void ln_tail(const GemmParams& p, float (&s1)[8], float 
     if (f.mode == 3 && f.g2 != nullptr && lane == 0) atomicAdd(&f.cnt2[group], 1u);   // keeps the second round's count complete
     return;
   }
-  ln_wait(f.cnt, group, lane);
+  if (!(f.dbg & 1)) ln_wait(f.cnt, group, lane);
+  if (f.dbg & 2) return;
   float mean[8], rstd[8];
   ln_row_stats(f.stats, warp_row0, rows_valid, lane, f.eps, mean, rstd);
   const float* xin = reinterpret_cast<const float*>(p.out);

@@ -49,6 +49,7 @@ struct LnFuse {
   const float *rope_cos, *rope_sin;   // [max_len, half_dim]
   int T, half_dim;
   float eps;
+  int dbg;                     // timing probes of tools/ln_probe.py only: 1 = skip the wait, 2 = stop after the exchange
 };
 
 // A_CONV  : implicit im2col of a 3x3 / stride-2 conv2d over channels-last [B, T1, F1, C]  (4-D strided TMA)

@@ -43,6 +43,10 @@ void launch_ctc_argmax(const float* enc, const float* W, const float* bias, int*
 void launch_ctc_collapse(const int* labels, const int* len, int B, int T, int blank, int* ids, int* frames, int* counts,
                          cudaStream_t s);
 
+// words.cu: (token id, frame) pairs -> word records (first frame, last frame + 1, first token, tokens) per utterance
+void launch_group_words(const int* ids, const int* frames, const int* counts, const unsigned char* flags, int B, int V, int max_out,
+                        int max_words, int* w_start, int* w_end, int* w_first, int* w_ntok, int* n_words, cudaStream_t s);
+
 // rnnt.cu
 void launch_sgemm_tn_bias(const float* A, const float* W, const float* bias, float* C, int M, int N, int K, cudaStream_t s);
 

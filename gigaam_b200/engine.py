@@ -401,6 +401,18 @@ class Engine:
         _lib.check(self.lib, self.handle, rc, "gam_greedy")
         return ids, frames, counts
 
+    def group_words(self, ids: Tensor, frames: Tensor, counts: Tensor, token_flags: Tensor):
+        """Device word grouping (gam_group_words): -> (word_start, word_end, word_first, word_ntok [B, max_out] i32, n_words [B] i32)."""
+        B, max_out = ids.shape
+        flags = token_flags.to(device=self.device, dtype=torch.uint8).contiguous()
+        outs = [torch.empty((B, max_out), dtype=torch.int32, device=self.device) for _ in range(4)]
+        n_words = torch.empty((B,), dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = self.lib.gam_group_words(self.handle, ids.data_ptr(), frames.data_ptr(), counts.data_ptr(), B, max_out, flags.data_ptr(),
+                                          flags.numel(), max_out, *[t.data_ptr() for t in outs], n_words.data_ptr(), self._stream())
+        _lib.check(self.lib, self.handle, rc, "gam_group_words")
+        return (*outs, n_words)
+
     def profile_begin(self) -> None:
         _lib.check(self.lib, self.handle, self.lib.gam_profile_begin(self.handle), "gam_profile_begin")
 

@@ -150,14 +150,24 @@ class GigaAMASR(GigaAM):
     def _decode(self, encoded: Tensor, encoded_len: Tensor, wav_lens: Tensor, word_timestamps: bool = False
                 ) -> List[Tuple[str, Optional[List[Word]]]]:
         """gigaam/model.py:96-124"""
-        decoded = self.decoding.decode(self.head, encoded, encoded_len)
         if not word_timestamps:
-            return [(t, None) for t, _, _ in decoded]
-        from .timestamps_utils import compute_frame_shift, frames_to_words
+            return [(t, None) for t, _, _ in self.decoding.decode(self.head, encoded, encoded_len)]
+        # tokens are grouped into words on the device (csrc/words.cu); one D2H copy brings ids and word records back
+        from .timestamps_utils import compute_frame_shift, token_flag_table, words_from_device
+        tok = self.decoding.tokenizer
+        if self.__dict__.get("_token_flags") is None:
+            self.__dict__["_token_flags"] = token_flag_table(tok)
+        ids, frames, counts = self.decoding.decode_device(self.head, encoded, encoded_len)
+        rec = self._get_engine().group_words(ids, frames, counts, self.__dict__["_token_flags"])
+        ids_h, counts_h, wl, el = ids.cpu(), counts.cpu().tolist(), wav_lens.cpu().tolist(), encoded_len.cpu().tolist()
+        ws, we, wf, wn, nw = (t.cpu() for t in rec)
         out: List[Tuple[str, Optional[List[Word]]]] = []
-        for i, (text, token_ids, token_frames) in enumerate(decoded):
-            shift = compute_frame_shift(int(wav_lens[i].item()), int(encoded_len[i].item()))
-            out.append((text, frames_to_words(self.decoding.tokenizer, token_ids, token_frames, shift)))
+        for i, n in enumerate(counts_h):
+            row = ids_h[i, :n].tolist()
+            k = int(nw[i])
+            shift = compute_frame_shift(int(wl[i]), int(el[i]))
+            words = words_from_device(tok, row, ws[i, :k].tolist(), we[i, :k].tolist(), wf[i, :k].tolist(), wn[i, :k].tolist(), shift)
+            out.append((tok.decode(row), words))
         return out
 
     @torch.inference_mode()

@@ -165,6 +165,29 @@ int gam_rnnt_greedy(gam_handle* h, const float* enc, const int32_t* enc_len, int
                     int64_t workspace_bytes, int32_t* ids, int32_t* frames, int32_t* counts, int32_t max_out,
                     void* stream);
 
+/* ---- the one multi-GPU exchange of the path: utterances are sharded over ranks, one process per GPU, and the
+ * device-resident hypotheses are all-gathered ONCE over NCCL (NVLink / NVSwitch) when the batch was actually split.
+ * gam_comm_unique_id: rank 0 fills 128 bytes, the host ships them to every rank by any channel (torch.distributed, MPI,
+ * a file); gam_comm_init: collective over all ranks, binds an NCCL communicator to the handle; gam_gather_hyps: every
+ * rank passes ONE packed int32 device buffer [ids B_local x W | frames B_local x W | counts B_local] of n_int32 elements
+ * (same n on every rank: pad short shards with counts = 0) and receives gathered[r * n_int32 ...] = rank r's buffer.
+ * Stream-ordered, capturable in a CUDA graph, no host synchronisation.  NCCL is bound at run time (dlopen): hosts without
+ * it keep every other entry point; these three then return an error. */
+int gam_comm_unique_id(uint8_t* out128);
+int gam_comm_init(gam_handle* h, const uint8_t* id128, int32_t rank, int32_t nranks);
+int32_t gam_comm_nccl_version(void);
+int gam_gather_hyps(gam_handle* h, const int32_t* packed, int64_t n_int32, int32_t* gathered, void* stream);
+
+/* Word grouping of hypotheses on the device  <- gigaam/timestamps_utils.py:13-53 frames_to_words (gigaam/model.py:104-124).
+ * ids / frames / counts as produced by gam_*_greedy (row pitch max_out); token_flags: device u8 [V], bit 0 = the piece is
+ * " " (delimiter), bit 1 = the piece starts with U+2581 (opens a new word), bit 2 = the piece (prefix removed) is empty
+ * after strip().  Per utterance b and word w < n_words[b] (row pitch max_words; max_words >= max_out is always enough):
+ * word_start = frame of the first piece, word_end = frame of the last piece + 1, and the pieces are tokens
+ * [word_first_token, word_first_token + word_tokens) of ids[b].  Times = frame * frame_shift on the host. */
+int gam_group_words(gam_handle* h, const int32_t* ids, const int32_t* frames, const int32_t* counts, int32_t B, int32_t max_out,
+                    const uint8_t* token_flags, int32_t V, int32_t max_words, int32_t* word_start, int32_t* word_end,
+                    int32_t* word_first_token, int32_t* word_tokens, int32_t* n_words, void* stream);
+
 /* ---- unit entry points (parity tests of the individual kernels) ---- */
 /* D[M,N] = A[M,K] W[N,K]^T with epilogue `kind` (0 bias->f16, 1 bias+silu->f16, 2 bias+glu->f16 [N/2 cols],
  * 3 res + scale*(acc+bias) -> f32, 4 bias -> f32).  A, W fp16 device; N % 256 == 0; K % 64 == 0. */

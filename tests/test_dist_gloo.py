@@ -19,7 +19,7 @@ def _worker(rank, world, port, batch, ret):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        T = 7 + rank                                  # ranks hold different row widths
+        T = 9                                         # row pitch: a function of the (shared) padded input length
         s, e = gdist.shard_bounds(batch, rank, world)
         ids = torch.zeros((e - s, T), dtype=torch.int32)
         frames = torch.zeros((e - s, T), dtype=torch.int32)
@@ -29,7 +29,9 @@ def _worker(rank, world, port, batch, ret):
             ids[i, :n] = torch.arange(u, u + n, dtype=torch.int32)
             frames[i, :n] = torch.arange(n, dtype=torch.int32) + 1
             counts[i] = n
-        gi, gf, gc = gdist.gather_hypotheses(ids, frames, counts, batch)
+        if e == s:                                    # empty shard (more ranks than utterances): still joins the gather
+            ids = frames = counts = None
+        gi, gf, gc = gdist.gather_hypotheses(ids, frames, counts, batch, T, torch.device("cpu"))
         ok = gi.shape[0] == batch
         for u in range(batch):
             n = u % 5
@@ -49,10 +51,24 @@ def test_shard_bounds_cover_the_batch():
             assert max(sizes) - min(sizes) <= 1
 
 
-def test_gather_hypotheses_world2_uneven():
-    world, batch = 2, 5
-    port = _free_port()
-    with mp.Manager() as mgr:
-        ret = mgr.dict()
-        mp.spawn(_worker, args=(world, port, batch, ret), nprocs=world, join=True)
-        assert dict(ret) == {0: True, 1: True}
+def test_gather_hypotheses_world2_uneven_and_empty_shard():
+    """One packed all-gather per call: an uneven split (5 utterances on 2 ranks) and a batch smaller than the world
+    (1 utterance on 2 ranks: rank 1's shard is empty and must neither hang nor corrupt the result)."""
+    world = 2
+    for batch in (5, 1):
+        port = _free_port()
+        with mp.Manager() as mgr:
+            ret = mgr.dict()
+            mp.spawn(_worker, args=(world, port, batch, ret), nprocs=world, join=True)
+            assert dict(ret) == {0: True, 1: True}, batch
+
+
+def test_pack_unpack_roundtrip():
+    rows, width, world, batch = 3, 4, 3, 7          # shards of 3, 2, 2
+    bufs = []
+    for r in range(world):
+        s, e = gdist.shard_bounds(batch, r, world)
+        ids = torch.arange(s * width, e * width, dtype=torch.int32).view(e - s, width)
+        bufs.append(gdist.pack_hypotheses(ids, ids + 1000, torch.arange(s, e, dtype=torch.int32), rows, width, "cpu"))
+    gi, gf, gc = gdist.unpack_gathered(torch.stack(bufs), batch, world, rows, width)
+    assert gi.flatten().tolist() == list(range(batch * width)) and torch.equal(gf, gi + 1000) and gc.tolist() == list(range(batch))

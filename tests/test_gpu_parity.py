@@ -375,6 +375,52 @@ def test_rnnt_large_batches_against_oracle_and_small_groups(which, B, eng_rnnt, 
         assert int(counts.sum()) > 0
 
 
+# ------------------------------------------------------------------------------------------ word grouping on the device
+class _Pieces:
+    """Stand-in tokenizer: id -> piece (charwise vocabularies and SentencePiece models both reduce to this)."""
+
+    def __init__(self, pieces):
+        self.pieces = pieces
+
+    def __len__(self):
+        return len(self.pieces)
+
+    def id_to_str(self, i):
+        return self.pieces[i]
+
+
+@pytest.mark.parametrize("kind", ["char", "sentencepiece"])
+def test_word_grouping_on_device_matches_reference_semantics(eng_ctc, dev, kind):
+    """gam_group_words (csrc/words.cu) against the host restatement of gigaam/timestamps_utils.py:13-53 on random
+    hypotheses: leading / trailing / repeated delimiters, bare U+2581 pieces, whitespace-only pieces, empty utterances,
+    utterances longer than one 32-token chunk."""
+    from gigaam_b200.timestamps_utils import frames_to_words, token_flag_table, words_from_device
+    if kind == "char":
+        tok = _Pieces([" "] + [chr(c) for c in range(ord("a"), ord("a") + 20)])
+    else:
+        tok = _Pieces(["\u2581", "\u2581ab", "cd", "\u2581e", "f", "\u2581 ", "g", "\u2581hij", "k", " ", "\t", "lm"])
+    g = torch.Generator().manual_seed(len(tok))
+    B, max_out = 9, 100
+    counts = torch.tensor([0, 1, 5, 31, 32, 33, 64, 100, 77], dtype=torch.int32)
+    p_delim = 0.25 if kind == "char" else 0.1
+    ids = torch.randint(1 if kind == "char" else 0, len(tok), (B, max_out), generator=g, dtype=torch.int32)
+    ids[torch.rand(B, max_out, generator=g) < p_delim] = 0 if kind == "char" else 9
+    ids[2, :5] = torch.tensor([0, 0, 3, 0, 0] if kind == "char" else [9, 0, 5, 10, 9], dtype=torch.int32)
+    frames = torch.sort(torch.randint(0, 400, (B, max_out), generator=g, dtype=torch.int32), dim=1).values
+    flags = token_flag_table(tok)
+    rec = eng_ctc.group_words(ids.to(dev), frames.to(dev), counts.to(dev), flags)
+    ws, we, wf, wn, nw = (t.cpu() for t in rec)
+    seen_words = 0
+    for b in range(B):
+        n, k = int(counts[b]), int(nw[b])
+        row = ids[b, :n].tolist()
+        want = frames_to_words(tok, row, frames[b, :n].tolist(), 0.04)
+        got = words_from_device(tok, row, ws[b, :k].tolist(), we[b, :k].tolist(), wf[b, :k].tolist(), wn[b, :k].tolist(), 0.04)
+        assert [(w.text, w.start, w.end) for w in got] == [(w.text, w.start, w.end) for w in want], b
+        seen_words += k
+    assert seen_words > 20
+
+
 # ------------------------------------------------------------------------------------------ public API (drop-in surface)
 def test_public_api_drop_in(dev, v2_ctc_ckpt):
     model = gigaam.load_model("v2_ctc", device=dev, checkpoint=v2_ctc_ckpt)     # reference default: fp16 encoder
