@@ -337,7 +337,7 @@ def main():
     e2e_value = world * B * args.steps / float(t[0].item())
     e2e_serial_value = world * B * args.steps / float(t[1].item())
     h2d = B * n_samples * 4 + B * 8
-    d2h = 2 * B * T * 4 + B * 4
+    d2h = 2 * B * T * 4 + 2 * B * 4      # ids, frames [B, T'] + counts, encoded_len [B], int32
 
     # ---- dominant kernel, timed live with CUDA events on the launching stream
     roofline = None

@@ -54,6 +54,7 @@ def load_model(model_name: str, fp16_encoder: bool = True, use_flash: Optional[b
     `{"cfg", "state_dict"}`; `synthetic=True` (or env GIGAAM_B200_SYNTHETIC=1) builds the seeded synthetic
     checkpoint of that model shape when `<download_root>/<name>.ckpt` does not exist."""
     device_obj = _normalize_device(device)
+    pack_cache_base = None
     if download_root is None:
         download_root = _CACHE_DIR
     if checkpoint is None:
@@ -72,6 +73,7 @@ def load_model(model_name: str, fp16_encoder: bool = True, use_flash: Optional[b
         path = os.path.join(download_root, model_name + ".ckpt")
         if os.path.isfile(path):
             checkpoint = _torch_load_ckpt(path)
+            pack_cache_base = os.path.join(download_root, f"{model_name}.{hash_path(path)[:16]}")
             if model_name == "v1_rnnt" or "e2e" in model_name:
                 checkpoint["cfg"]["decoding"]["model_path"] = os.path.join(download_root, model_name + "_tokenizer.model")
         else:
@@ -88,6 +90,7 @@ def load_model(model_name: str, fp16_encoder: bool = True, use_flash: Optional[b
     model = GigaAM(cfg) if "ssl" in model_name else GigaAMASR(cfg)
     model.load_state_dict(checkpoint["state_dict"])
     model = model.eval()
+    model.__dict__["_pack_cache_base"] = pack_cache_base    # packed-weight cache next to the checkpoint (model.py)
     if device_obj.type == "cpu":
         logging.warning("gigaam_b200 has no CPU compute path; the model is constructed but forward() needs CUDA")
     if fp16_encoder and device_obj.type != "cpu":

@@ -81,26 +81,6 @@ __device__ __forceinline__ void ln_wait(const unsigned int* cnt, int group, int 
   __syncwarp();
 }
 
-__device__ __forceinline__ void ln_row_stats(const float2* stats, long long warp_row0, int rows_valid, int lane, float eps,
-                                             float (&mean)[8], float (&rstd)[8]) {
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int r = i * 4 + (lane >> 3);
-    float s = 0.f, q = 0.f;
-    if (r < rows_valid) {
-      const float2* sp = stats + (warp_row0 + r) * kLnSlots;
-#pragma unroll
-      for (int j = 0; j < kLnSlots; ++j) {   // fixed order: bit-reproducible
-        const float2 v = __ldcg(sp + j);
-        s += v.x;
-        q += v.y;
-      }
-    }
-    mean[i] = s * (1.0f / kLnD);
-    rstd[i] = rsqrtf(fmaxf(q * (1.0f / kLnD) - mean[i] * mean[i], 0.f) + eps);
-  }
-}
-
 __device__ __forceinline__ uint2 ln_pack4(float4 v) {
   return make_uint2(pack_half2(v.x, v.y), pack_half2(v.z, v.w));
 }
@@ -109,119 +89,207 @@ __device__ __forceinline__ float4 ln_affine(float4 v, float mean, float rstd, fl
                      (v.w - mean) * rstd * g.w + b.w);
 }
 
-// 8 independent 16-byte L2 loads (one per row of this thread) issued back to back.  The passes below always load a whole
-// chunk BEFORE they store anything: xin / out16 / xout are not __restrict__ (xout really aliases xin in mode 3), so a store
-// between two loads would serialise them at one L2 round trip each (measured: 22 us per tile instead of ~4)
-__device__ __forceinline__ void ln_load8(const float* base, size_t pitch, long long warp_row0, int rows_valid, int col, int lane,
-                                         float4 (&v)[8]) {
+// The passes below are latency bound (8 epilogue warps per SM against a ~1 us loaded L2 round trip), so each one works on
+// half of the thread's rows at a time and issues ALL loads of that half -- 16 x 16 bytes per thread, 64 KB in flight per
+// SM -- before it touches the first value, and never stores between two loads: xin / out16 / xout are not __restrict__
+// (xout really aliases xin in mode 3), so a store in between would serialise the loads at one L2 round trip each.
+// One noinline function per mode: each gets its own register allocation, away from the main epilogue's accumulators.
+struct LnRows {
+  float mean[4], rstd[4];
+};
+
+// rows i = 4 * h + j (j = 0..3) of this thread: global row warp_row0 + i * 4 + (lane >> 3)
+__device__ __forceinline__ void ln_half_stats(const float2* stats, long long warp_row0, int rows_valid, int lane, float eps, int h,
+                                              LnRows& st) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int r = i * 4 + (lane >> 3);
-    v[i] = r < rows_valid ? __ldcg(reinterpret_cast<const float4*>(base + static_cast<size_t>(warp_row0 + r) * pitch + col))
-                          : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int j = 0; j < 4; ++j) {
+    const int r = (4 * h + j) * 4 + (lane >> 3);
+    float s = 0.f, q = 0.f;
+    if (r < rows_valid) {
+      const float2* sp = stats + (warp_row0 + r) * kLnSlots;
+#pragma unroll
+      for (int k = 0; k < kLnSlots; ++k) {   // fixed order: bit-reproducible
+        const float2 v = __ldcg(sp + k);
+        s += v.x;
+        q += v.y;
+      }
+    }
+    st.mean[j] = s * (1.0f / kLnD);
+    st.rstd[j] = rsqrtf(fmaxf(q * (1.0f / kLnD) - st.mean[j] * st.mean[j], 0.f) + eps);
   }
 }
 
-__device__ __noinline__ void ln_tail(const GemmParams& p, float (&s1)[8], float (&s2)[8], long long warp_row0, int rows_valid,
-                                     int group, int n_blk, int half, int lane) {
+__device__ __forceinline__ void ln_load_half(const float* base, size_t pitch, long long warp_row0, int rows_valid, int col0, int lane,
+                                             int h, float4 (&v)[4][4]) {
+#pragma unroll
+  for (int ci = 0; ci < 4; ++ci)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = (4 * h + j) * 4 + (lane >> 3);
+      v[ci][j] = r < rows_valid ? __ldcg(reinterpret_cast<const float4*>(base + static_cast<size_t>(warp_row0 + r) * pitch + col0 + ci * 32))
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+// mode 1: out16 = LN(x)
+__device__ __noinline__ void ln_mode1(const GemmParams& p, long long warp_row0, int rows_valid, int col0, int lane) {
   const LnFuse& f = p.ln;
-  const int slot = 2 * n_blk + half;
-  const int col0 = n_blk * 256 + half * 128 + (lane & 7) * 4;   // + 32 * chunk
-  ln_publish(s1, s2, f.stats, f.cnt, warp_row0, rows_valid, group, slot, lane);
-  if (rows_valid <= 0) {
-    if (f.mode == 3 && f.g2 != nullptr && lane == 0) atomicAdd(&f.cnt2[group], 1u);   // keeps the second round's count complete
-    return;
-  }
-  if (!(f.dbg & 1)) ln_wait(f.cnt, group, lane);
-  if (f.dbg & 2) return;
-  float mean[8], rstd[8];
-  ln_row_stats(f.stats, warp_row0, rows_valid, lane, f.eps, mean, rstd);
   const float* xin = reinterpret_cast<const float*>(p.out);
-  const size_t ldx = static_cast<size_t>(p.ldo);
-  float4 v[2][8];          // chunk ci in v[ci & 1], chunk ci + 1 in flight
-  if (f.mode == 1 || f.mode == 2) {
-    float4 vp[8];          // rotary partner columns (mode 2)
-    ln_load8(xin, ldx, warp_row0, rows_valid, col0, lane, v[0]);
+#pragma unroll 1
+  for (int h = 0; h < 2; ++h) {
+    float4 v[4][4];
+    ln_load_half(xin, static_cast<size_t>(p.ldo), warp_row0, rows_valid, col0, lane, h, v);
+    LnRows st;
+    ln_half_stats(f.stats, warp_row0, rows_valid, lane, f.eps, h, st);
 #pragma unroll
     for (int ci = 0; ci < 4; ++ci) {
       const int col = col0 + ci * 32;
-      // rotary partner: the float4 24 columns away inside the same 48-wide head (utils.py:83-100); it may belong to
-      // another CTA's tile -- visible, because all six slots of these rows have been published
-      const int q = col % 48;
-      const bool lo = q < 24;
-      const int colp = lo ? col + 24 : col - 24;
-      if (f.mode == 2) ln_load8(xin, ldx, warp_row0, rows_valid, colp, lane, vp);
-      if (ci + 1 < 4) ln_load8(xin, ldx, warp_row0, rows_valid, col + 32, lane, v[(ci + 1) & 1]);
       const float4 g = __ldg(reinterpret_cast<const float4*>(f.g + col));
       const float4 b = __ldg(reinterpret_cast<const float4*>(f.b + col));
-      float4 gp = g, bp = b;
-      if (f.mode == 2) {
-        gp = __ldg(reinterpret_cast<const float4*>(f.g + colp));
-        bp = __ldg(reinterpret_cast<const float4*>(f.b + colp));
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int r = (4 * h + j) * 4 + (lane >> 3);
+        if (r < rows_valid)
+          *reinterpret_cast<uint2*>(f.out16 + static_cast<size_t>(warp_row0 + r) * kLnD + col) =
+              ln_pack4(ln_affine(v[ci][j], st.mean[j], st.rstd[j], g, b));
+      }
+    }
+  }
+}
+
+// mode 2: out16 = u = LN(x), rope16 = rotary(u).  The rotary partner of a float4 is the float4 24 columns away inside the
+// same 48-wide head (utils.py:83-100); it may belong to another CTA's tile -- visible, because all six slots of these
+// rows have been published.
+__device__ __noinline__ void ln_mode2(const GemmParams& p, long long warp_row0, int rows_valid, int col0, int lane) {
+  const LnFuse& f = p.ln;
+  const float* xin = reinterpret_cast<const float*>(p.out);
+  const size_t ldx = static_cast<size_t>(p.ldo);
+#pragma unroll 1
+  for (int h = 0; h < 2; ++h) {
+    LnRows st;
+    ln_half_stats(f.stats, warp_row0, rows_valid, lane, f.eps, h, st);
+    int trow[4];           // frame index t = row mod T of each row
+#pragma unroll
+    for (int j = 0; j < 4; ++j) trow[j] = static_cast<int>((warp_row0 + (4 * h + j) * 4 + (lane >> 3)) % f.T);
+#pragma unroll 1
+    for (int cp = 0; cp < 2; ++cp) {     // two chunks at a time: 8 own + 8 partner loads in flight
+      float4 v[2][4], vp[2][4];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int col = col0 + (cp * 2 + c) * 32;
+        const int colp = (col % 48) < 24 ? col + 24 : col - 24;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int r = (4 * h + j) * 4 + (lane >> 3);
+          const bool ok = r < rows_valid;
+          const float* rowp = xin + static_cast<size_t>(warp_row0 + r) * ldx;
+          v[c][j] = ok ? __ldcg(reinterpret_cast<const float4*>(rowp + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          vp[c][j] = ok ? __ldcg(reinterpret_cast<const float4*>(rowp + colp)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
       }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r = i * 4 + (lane >> 3);
-        if (r < rows_valid) {
-          const size_t row = static_cast<size_t>(warp_row0 + r);
-          const float4 u = ln_affine(v[ci & 1][i], mean[i], rstd[i], g, b);
-          *reinterpret_cast<uint2*>(f.out16 + row * kLnD + col) = ln_pack4(u);
-          if (f.mode == 2) {
-            const float4 up = ln_affine(vp[i], mean[i], rstd[i], gp, bp);
-            const int t = static_cast<int>(row % static_cast<size_t>(f.T));
-            const float4 c = __ldg(reinterpret_cast<const float4*>(f.rope_cos + static_cast<size_t>(t) * f.half_dim + (lo ? q : q - 24)));
-            const float4 s = __ldg(reinterpret_cast<const float4*>(f.rope_sin + static_cast<size_t>(t) * f.half_dim + (lo ? q : q - 24)));
-            const float sg = lo ? -1.f : 1.f;
+      for (int c = 0; c < 2; ++c) {
+        const int col = col0 + (cp * 2 + c) * 32;
+        const int q = col % 48;
+        const bool lo = q < 24;
+        const int colp = lo ? col + 24 : col - 24;
+        const float4 g = __ldg(reinterpret_cast<const float4*>(f.g + col));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(f.b + col));
+        const float4 gp = __ldg(reinterpret_cast<const float4*>(f.g + colp));
+        const float4 bp = __ldg(reinterpret_cast<const float4*>(f.b + colp));
+        const float sg = lo ? -1.f : 1.f;
+        const int qo = lo ? q : q - 24;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int r = (4 * h + j) * 4 + (lane >> 3);
+          if (r < rows_valid) {
+            const size_t row = static_cast<size_t>(warp_row0 + r);
+            const float4 u = ln_affine(v[c][j], st.mean[j], st.rstd[j], g, b);
+            const float4 up = ln_affine(vp[c][j], st.mean[j], st.rstd[j], gp, bp);
+            const float4 cs = __ldg(reinterpret_cast<const float4*>(f.rope_cos + static_cast<size_t>(trow[j]) * f.half_dim + qo));
+            const float4 sn = __ldg(reinterpret_cast<const float4*>(f.rope_sin + static_cast<size_t>(trow[j]) * f.half_dim + qo));
+            *reinterpret_cast<uint2*>(f.out16 + row * kLnD + col) = ln_pack4(u);
             *reinterpret_cast<uint2*>(f.rope16 + row * kLnD + col) =
-                ln_pack4(make_float4(fmaf(sg * up.x, s.x, u.x * c.x), fmaf(sg * up.y, s.y, u.y * c.y), fmaf(sg * up.z, s.z, u.z * c.z),
-                                     fmaf(sg * up.w, s.w, u.w * c.w)));
+                ln_pack4(make_float4(fmaf(sg * up.x, sn.x, u.x * cs.x), fmaf(sg * up.y, sn.y, u.y * cs.y),
+                                     fmaf(sg * up.z, sn.z, u.z * cs.z), fmaf(sg * up.w, sn.w, u.w * cs.w)));
           }
         }
       }
     }
-    return;
   }
-  // mode 3: xout = LN(x) in fp32 (norm_out, encoder.py:497), then -- unless this is the last layer -- the next layer's
-  // first LayerNorm of that result, with a second statistics round
+}
+
+// mode 3: xout = LN(x) in fp32 (norm_out, encoder.py:497), then -- unless this is the last layer -- the next layer's
+// first LayerNorm of that result, with a second statistics round
+__device__ __noinline__ void ln_mode3(const GemmParams& p, long long warp_row0, int rows_valid, int group, int slot, int col0, int lane) {
+  const LnFuse& f = p.ln;
+  const float* xin = reinterpret_cast<const float*>(p.out);
+  float s1[8], s2[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
-  ln_load8(xin, ldx, warp_row0, rows_valid, col0, lane, v[0]);
 #pragma unroll
-  for (int ci = 0; ci < 4; ++ci) {
-    const int col = col0 + ci * 32;
-    if (ci + 1 < 4) ln_load8(xin, ldx, warp_row0, rows_valid, col + 32, lane, v[(ci + 1) & 1]);
-    const float4 g = __ldg(reinterpret_cast<const float4*>(f.g + col));
-    const float4 b = __ldg(reinterpret_cast<const float4*>(f.b + col));
+  for (int h = 0; h < 2; ++h) {
+    float4 v[4][4];
+    ln_load_half(xin, static_cast<size_t>(p.ldo), warp_row0, rows_valid, col0, lane, h, v);
+    LnRows st;
+    ln_half_stats(f.stats, warp_row0, rows_valid, lane, f.eps, h, st);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int r = i * 4 + (lane >> 3);
-      if (r < rows_valid) {
-        const float4 y = ln_affine(v[ci & 1][i], mean[i], rstd[i], g, b);
-        *reinterpret_cast<float4*>(f.xout + static_cast<size_t>(warp_row0 + r) * kLnD + col) = y;
-        s1[i] += (y.x + y.y) + (y.z + y.w);
-        s2[i] = fmaf(y.x, y.x, fmaf(y.y, y.y, fmaf(y.z, y.z, fmaf(y.w, y.w, s2[i]))));
+    for (int ci = 0; ci < 4; ++ci) {
+      const int col = col0 + ci * 32;
+      const float4 g = __ldg(reinterpret_cast<const float4*>(f.g + col));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(f.b + col));
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int r = (4 * h + j) * 4 + (lane >> 3);
+        if (r < rows_valid) {
+          const float4 y = ln_affine(v[ci][j], st.mean[j], st.rstd[j], g, b);
+          *reinterpret_cast<float4*>(f.xout + static_cast<size_t>(warp_row0 + r) * kLnD + col) = y;
+          s1[4 * h + j] += (y.x + y.y) + (y.z + y.w);
+          s2[4 * h + j] = fmaf(y.x, y.x, fmaf(y.y, y.y, fmaf(y.z, y.z, fmaf(y.w, y.w, s2[4 * h + j]))));
+        }
       }
     }
   }
   if (f.g2 == nullptr) return;
   ln_publish(s1, s2, f.stats2, f.cnt2, warp_row0, rows_valid, group, slot, lane);
   ln_wait(f.cnt2, group, lane);
-  ln_row_stats(f.stats2, warp_row0, rows_valid, lane, f.eps, mean, rstd);
-  ln_load8(f.xout, kLnD, warp_row0, rows_valid, col0, lane, v[0]);
+#pragma unroll 1
+  for (int h = 0; h < 2; ++h) {
+    float4 v[4][4];
+    ln_load_half(f.xout, kLnD, warp_row0, rows_valid, col0, lane, h, v);
+    LnRows st;
+    ln_half_stats(f.stats2, warp_row0, rows_valid, lane, f.eps, h, st);
 #pragma unroll
-  for (int ci = 0; ci < 4; ++ci) {
-    const int col = col0 + ci * 32;
-    if (ci + 1 < 4) ln_load8(f.xout, kLnD, warp_row0, rows_valid, col + 32, lane, v[(ci + 1) & 1]);
-    const float4 g = __ldg(reinterpret_cast<const float4*>(f.g2 + col));
-    const float4 b = __ldg(reinterpret_cast<const float4*>(f.b2 + col));
+    for (int ci = 0; ci < 4; ++ci) {
+      const int col = col0 + ci * 32;
+      const float4 g = __ldg(reinterpret_cast<const float4*>(f.g2 + col));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(f.b2 + col));
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int r = i * 4 + (lane >> 3);
-      if (r < rows_valid)
-        *reinterpret_cast<uint2*>(f.out16 + static_cast<size_t>(warp_row0 + r) * kLnD + col) =
-            ln_pack4(ln_affine(v[ci & 1][i], mean[i], rstd[i], g, b));
+      for (int j = 0; j < 4; ++j) {
+        const int r = (4 * h + j) * 4 + (lane >> 3);
+        if (r < rows_valid)
+          *reinterpret_cast<uint2*>(f.out16 + static_cast<size_t>(warp_row0 + r) * kLnD + col) =
+              ln_pack4(ln_affine(v[ci][j], st.mean[j], st.rstd[j], g, b));
+      }
     }
   }
+}
+
+// everything after the first publish: wait for the row statistics, then the normalisation pass(es)
+__device__ __forceinline__ void ln_tail(const GemmParams& p, long long warp_row0, int rows_valid, int group, int n_blk, int half,
+                                        int lane) {
+  const LnFuse& f = p.ln;
+  const int slot = 2 * n_blk + half;
+  const int col0 = n_blk * 256 + half * 128 + (lane & 7) * 4;   // + 32 * chunk
+  if (rows_valid <= 0) {
+    if (f.mode == 3 && f.g2 != nullptr && lane == 0) atomicAdd(&f.cnt2[group], 1u);   // keeps the second round's count complete
+    return;
+  }
+  if (!(f.dbg & 1)) ln_wait(f.cnt, group, lane);
+  if (f.dbg & 2) return;
+  if (f.mode == 1) ln_mode1(p, warp_row0, rows_valid, col0, lane);
+  else if (f.mode == 2) ln_mode2(p, warp_row0, rows_valid, col0, lane);
+  else ln_mode3(p, warp_row0, rows_valid, group, slot, col0, lane);
 }
 
 template <int EPI, int AMODE>
@@ -485,7 +553,8 @@ gemm2_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive_cluster(&tmem_empty[acc], 0);
-          ln_tail(p, ls1, ls2, warp_row0, rows_valid, m_blk * 4 + quad, n_blk, half, lane);
+          ln_publish(ls1, ls2, p.ln.stats, p.ln.cnt, warp_row0, rows_valid, m_blk * 4 + quad, 2 * n_blk + half, lane);
+          ln_tail(p, warp_row0, rows_valid, m_blk * 4 + quad, n_blk, half, lane);
         }
       } else if constexpr (EPI == EPI_POWER_F32) {
         // |X|^2 of a DFT whose cos rows fill accumulator columns [0,128) and sin rows [128,256) of the tile

@@ -6,7 +6,10 @@ from __future__ import annotations
 
 import collections
 import ctypes as C
+import hashlib
+import json
 import math
+import os
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -129,7 +132,13 @@ class Engine:
 
     WS_CACHE = 4      # workspaces kept per kind (distinct batch shapes)
 
-    def __init__(self, cfg: Dict, state_dict: Dict[str, Tensor], device: torch.device):
+    PACK_FORMAT = 3   # bump when the packing order / layouts below change
+
+    def __init__(self, cfg: Dict, state_dict: Dict[str, Tensor], device: torch.device, pack_cache: Optional[str] = None):
+        """`pack_cache`: path of an on-disk cache of the re-laid-out weights.  When it exists and matches
+        this cfg the load-time re-layout (BN folding, concatenations, permutations, fp16 casts, tables) is skipped and the
+        packed tensors are uploaded as stored; otherwise it is written after packing.  Callers key the path by the
+        checkpoint's md5 (load_model does)."""
         if device.type != "cuda":
             raise RuntimeError("gigaam_b200 runs on CUDA (sm_100a) devices only; there is no CPU path")
         if device.index is None:      # an index-less "cuda" means the CURRENT device, not GPU 0
@@ -138,6 +147,13 @@ class Engine:
         self.device = device
         self.cfg = cfg
         self._keep: List[Tensor] = []
+        self._pack_sig = hashlib.sha256(json.dumps([self.PACK_FORMAT, cfg], sort_keys=True, default=str).encode()).hexdigest()
+        self._pack_in: Optional[List[Tensor]] = None      # tensors replayed from the cache, in _dev() call order
+        self._pack_out: Optional[List[Tensor]] = None     # tensors recorded for the cache
+        if pack_cache is not None:
+            self._pack_in = self._read_pack_cache(pack_cache)
+            if self._pack_in is None:
+                self._pack_out = []
         self._ws_enc = _WorkspaceCache(self.WS_CACHE)
         self._ws_mel = _WorkspaceCache(self.WS_CACHE)
         self._ws_dec = _WorkspaceCache(self.WS_CACHE)
@@ -191,15 +207,45 @@ class Engine:
         with torch.cuda.device(device):
             rc = self.lib.gam_create(C.byref(gc), C.byref(gw), device.index, C.byref(self.handle))
         _lib.check(self.lib, self.handle, rc, "gam_create")
+        if self._pack_out is not None:
+            self._write_pack_cache(pack_cache)
+        self.pack_cache_hit = self._pack_in is not None
+        self._pack_in = self._pack_out = None
 
     # ------------------------------------------------------------------ packing helpers
-    def _dev(self, t: Tensor, dtype: Optional[torch.dtype] = None) -> int:
-        t = t.detach()
-        if dtype is not None:
-            t = t.to(dtype)
+    def _dev(self, t, dtype: Optional[torch.dtype] = None) -> int:
+        """Upload one packed tensor (or, given a callable, the tensor it computes) and keep it alive; returns the device
+        pointer.  With a cache hit the stored tensor of this call position is uploaded and `t` is never evaluated."""
+        if self._pack_in is not None:
+            t = self._pack_in[len(self._keep)]
+        else:
+            t = (t() if callable(t) else t).detach()
+            if dtype is not None:
+                t = t.to(dtype)
+            if self._pack_out is not None:
+                self._pack_out.append(t.cpu().contiguous())
         t = t.to(self.device).contiguous()
         self._keep.append(t)
         return t.data_ptr()
+
+    def _read_pack_cache(self, path: str) -> Optional[List[Tensor]]:
+        if not os.path.isfile(path):
+            return None
+        try:
+            blob = torch.load(path, map_location="cpu", weights_only=True)
+            if blob.get("signature") == self._pack_sig and isinstance(blob.get("tensors"), list):
+                return blob["tensors"]
+        except Exception:
+            pass
+        return None          # stale or unreadable: repack and overwrite
+
+    def _write_pack_cache(self, path: str) -> None:
+        try:
+            tmp = f"{path}.tmp{os.getpid()}"
+            torch.save({"signature": self._pack_sig, "tensors": self._pack_out}, tmp)
+            os.replace(tmp, path)
+        except OSError:
+            pass             # a read-only cache directory must not break loading
 
     def _pack_frontend(self, gw, sd):
         n = self.n_fft
@@ -216,7 +262,7 @@ class Engine:
         gw.mel_fb = self._dev(fb)
         # tensor-core front end: split-precision DFT basis + bin range of every mel filter
         if K <= 256:
-            gw.dft_w = self._dev(split_dft_basis(n))
+            gw.dft_w = self._dev(lambda: split_dft_basis(n))
             nz = fb != 0
             lo = torch.where(nz.any(0), nz.float().argmax(0), torch.zeros(fb.shape[1], dtype=torch.long))
             hi = torch.where(nz.any(0), fb.shape[0] - nz.flip(0).float().argmax(0), torch.zeros(fb.shape[1], dtype=torch.long))
@@ -241,10 +287,10 @@ class Engine:
         gw.sub1_w = self._dev(w1.reshape(d, 9))
         gw.sub1_b = self._dev(sd[p + "conv.0.bias"].float())
         w2 = sd[p + "conv.2.weight"].float()                     # [C_out, C_in, kt, kf]
-        gw.sub2_w = self._dev(pack_conv2_weight(w2), torch.float16)
+        gw.sub2_w = self._dev(lambda: pack_conv2_weight(w2), torch.float16)
         gw.sub2_b = self._dev(sd[p + "conv.2.bias"].float())
         wo = sd[p + "out.weight"].float()                        # [d, C*F2] with K index c*F2 + f
-        gw.sub_out_w = self._dev(pack_sub_out_weight(wo, d), torch.float16)
+        gw.sub_out_w = self._dev(lambda: pack_sub_out_weight(wo, d), torch.float16)
         gw.sub_out_b = self._dev(sd[p + "out.bias"].float())
 
     def _pack_rope(self, gw, enc):
@@ -273,7 +319,7 @@ class Engine:
                                       f("self_attn.pos_bias_u"), f("self_attn.pos_bias_v"))
             lw.w_qkv_rel, lw.b_qkv_rel = self._dev(w4, h16), self._dev(b4)
             # linear_pos (no bias, encoder.py:198,219) of a constant table is a constant: projected once at load time
-            lw.pos_proj = self._dev(self._pos_emb @ f("self_attn.linear_pos.weight").to(self.device).t(), h16)
+            lw.pos_proj = self._dev(lambda: self._pos_emb @ f("self_attn.linear_pos.weight").to(self.device).t(), h16)
             lw.w_qk = lw.b_qk = lw.w_v = lw.b_v = None
         else:
             # [W_q ; W_k ; W_v] and their biases in ONE allocation each: w_v / b_v point behind w_qk / b_qk, which lets the

@@ -60,24 +60,39 @@ def split_on_energy(wav: Tensor, sample_rate: int = SAMPLE_RATE, max_duration: f
 
 def transcribe_segments(model, segments: Sequence[Tensor], boundaries: Sequence[Tuple[float, float]], word_timestamps: bool = False,
                         batch_size: int = 16) -> LongformTranscriptionResult:
-    """Batched inference over pre-cut segments, results in the original order (gigaam/model.py:222-259)."""
+    """Batched inference over pre-cut segments, results in the original order (gigaam/model.py:222-259).  The
+    length-bucketed batches go through `pipeline.BatchPipeline`: the upload of batch i+1 and the read-back of batch i-1
+    overlap the kernels of batch i, recurring shapes replay a CUDA graph, and word grouping stays on the device."""
+    from .pipeline import BatchPipeline
     if len(segments) != len(boundaries):
         raise ValueError("segments and boundaries differ in length")
     if not segments:
         return LongformTranscriptionResult(segments=[])
     lengths = [int(s.numel()) for s in segments]
     out: List[Optional[Segment]] = [None] * len(segments)
-    dev, dtype = model._device, model._dtype
-    for batch in plan_batches(lengths, batch_size):
-        longest = max(lengths[i] for i in batch)
-        wav = torch.zeros((len(batch), longest), dtype=torch.float32)
-        for row, i in enumerate(batch):
-            wav[row, : lengths[i]] = segments[i].reshape(-1).float().cpu()
-        wav_lens = torch.tensor([lengths[i] for i in batch], dtype=torch.int64)
-        wav_d = wav.pin_memory().to(dev, non_blocking=True).to(dtype)      # same fp16 rounding of the waveform as model.py:239
-        lens_d = wav_lens.to(dev)
-        encoded, encoded_len = model.forward(wav_d, lens_d)
-        for row, (text, words) in enumerate(model._decode(encoded, encoded_len, lens_d, word_timestamps)):
+    dtype = model._dtype
+    batches = plan_batches(lengths, batch_size)
+
+    def host_batches():
+        for batch in batches:
+            longest = max(lengths[i] for i in batch)
+            wav = torch.zeros((len(batch), longest), dtype=torch.float32)
+            for row, i in enumerate(batch):
+                # same fp16 rounding of the waveform as gigaam/model.py:239 (`.to(self._dtype)`)
+                wav[row, : lengths[i]] = segments[i].reshape(-1).float().cpu().to(dtype).float()
+            yield wav.pin_memory(), torch.tensor([lengths[i] for i in batch], dtype=torch.int64)
+
+    # a graph per distinct (batch, padded length) only pays off when shapes recur; VAD segments rarely do
+    shapes = [(len(b), max(lengths[i] for i in b)) for b in batches]
+    pipe = BatchPipeline(model, use_graph=len(set(shapes)) < len(shapes), with_words=word_timestamps)
+    for batch, host in zip(batches, pipe.run_raw(host_batches())):
+        ids, frames, counts, enc_len = host[:4]
+        if word_timestamps:
+            wav_lens = torch.tensor([lengths[i] for i in batch])
+            results = model._words_from_records(ids, counts, enc_len, wav_lens, list(host[4:]))
+        else:
+            results = [(t, None) for t, _, _ in model.decoding.to_hypotheses(ids, frames, counts)]
+        for row, (text, words) in enumerate(results):
             i = batch[row]
             seg_start, seg_end = boundaries[i]
             shifted = None

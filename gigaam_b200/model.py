@@ -82,9 +82,15 @@ class GigaAM(nn.Module):
             if dev.type != "cuda":
                 raise RuntimeError("gigaam_b200 has no CPU path: move the model to a CUDA (sm_100a) device first")
             sd = {k: v for k, v in self.state_dict().items()}
-            eng = Engine(self._engine_cfg(), sd, dev)
+            eng = Engine(self._engine_cfg(), sd, dev, pack_cache=self._pack_cache_path())
             self.__dict__["_engine_obj"] = eng
         return eng
+
+    def _pack_cache_path(self) -> Optional[str]:
+        """On-disk cache of the packed weights, set by load_model for checkpoints read from a file: keyed by the
+        checkpoint's md5 and the parameter dtype the engine was built from (fp16_encoder rounds before packing)."""
+        base = self.__dict__.get("_pack_cache_base")
+        return None if base is None else f"{base}.{str(self._dtype).split('.')[-1]}.b200pack"
 
     def _engine_cfg(self) -> Dict:
         c = self._ncfg
@@ -153,19 +159,28 @@ class GigaAMASR(GigaAM):
         if not word_timestamps:
             return [(t, None) for t, _, _ in self.decoding.decode(self.head, encoded, encoded_len)]
         # tokens are grouped into words on the device (csrc/words.cu); one D2H copy brings ids and word records back
-        from .timestamps_utils import compute_frame_shift, token_flag_table, words_from_device
-        tok = self.decoding.tokenizer
-        if self.__dict__.get("_token_flags") is None:
-            self.__dict__["_token_flags"] = token_flag_table(tok)
         ids, frames, counts = self.decoding.decode_device(self.head, encoded, encoded_len)
-        rec = self._get_engine().group_words(ids, frames, counts, self.__dict__["_token_flags"])
-        ids_h, counts_h, wl, el = ids.cpu(), counts.cpu().tolist(), wav_lens.cpu().tolist(), encoded_len.cpu().tolist()
-        ws, we, wf, wn, nw = (t.cpu() for t in rec)
+        rec = self._get_engine().group_words(ids, frames, counts, self._word_flags())
+        return self._words_from_records(ids.cpu(), counts.cpu(), encoded_len.cpu(), wav_lens.cpu(), [t.cpu() for t in rec])
+
+    def _word_flags(self) -> Tensor:
+        """Per-token flag table of the device word grouping (timestamps_utils.token_flag_table), built once."""
+        if self.__dict__.get("_token_flags") is None:
+            from .timestamps_utils import token_flag_table
+            self.__dict__["_token_flags"] = token_flag_table(self.decoding.tokenizer)
+        return self.__dict__["_token_flags"]
+
+    def _words_from_records(self, ids: Tensor, counts: Tensor, encoded_len: Tensor, wav_lens: Tensor, rec: List[Tensor]
+                            ) -> List[Tuple[str, Optional[List[Word]]]]:
+        """Host copies of (ids, counts, encoded_len, wav_lens, gam_group_words records) -> [(text, words)] per utterance."""
+        from .timestamps_utils import compute_frame_shift, words_from_device
+        tok = self.decoding.tokenizer
+        ws, we, wf, wn, nw = rec
         out: List[Tuple[str, Optional[List[Word]]]] = []
-        for i, n in enumerate(counts_h):
-            row = ids_h[i, :n].tolist()
+        for i, n in enumerate(counts.tolist()):
+            row = ids[i, :n].tolist()
             k = int(nw[i])
-            shift = compute_frame_shift(int(wl[i]), int(el[i]))
+            shift = compute_frame_shift(int(wav_lens[i]), int(encoded_len[i]))
             words = words_from_device(tok, row, ws[i, :k].tolist(), we[i, :k].tolist(), wf[i, :k].tolist(), wn[i, :k].tolist(), shift)
             out.append((tok.decode(row), words))
         return out

@@ -16,7 +16,8 @@ Tensor = torch.Tensor
 class _ShapeGraph:
     """The whole device step for one (B, N) input shape, captured once: static inputs -> static outputs."""
 
-    def __init__(self, model, B: int, N: int, dev: torch.device):
+    def __init__(self, model, B: int, N: int, dev: torch.device, with_words: bool = False):
+        self.with_words = with_words
         self.wav = torch.zeros((B, N), dtype=torch.float32, device=dev)
         self.len = torch.full((B,), N, dtype=torch.int64, device=dev)
         side = torch.cuda.Stream(device=dev)
@@ -34,13 +35,25 @@ class _ShapeGraph:
         self._held = model._get_engine().held_workspaces(B, N)
 
     def _step(self, model):
-        enc, enc_len = model(self.wav, self.len)
-        return model.decoding.decode_device(model.head, enc, enc_len)
+        return device_step(model, self.wav, self.len, self.with_words)
+
+
+def device_step(model, wav: Tensor, lengths: Tensor, with_words: bool = False):
+    """wav -> device-resident hypotheses (ids, frames, counts, encoded_len[, word records]): the kernels of one batch."""
+    enc, enc_len = model(wav, lengths)
+    ids, frames, counts = model.decoding.decode_device(model.head, enc, enc_len)
+    if not with_words:
+        return ids, frames, counts, enc_len
+    return (ids, frames, counts, enc_len) + tuple(model._get_engine().group_words(ids, frames, counts, model._word_flags()))
 
 
 class BatchPipeline:
-    def __init__(self, model, use_graph: bool = True, max_graphs: int = 4):
+    """`run(host_batches)` yields the hypotheses of every batch.  `with_words=True` also groups tokens into words on the
+    device (csrc/words.cu) and `run_raw` then yields the host copies of the raw records for word timestamps."""
+
+    def __init__(self, model, use_graph: bool = True, max_graphs: int = 4, with_words: bool = False):
         self.model = model
+        self.with_words = with_words
         self.dev = model._device
         self.copy_stream = torch.cuda.Stream(device=self.dev)
         self.use_graph = use_graph
@@ -61,13 +74,20 @@ class BatchPipeline:
         if g is None:
             if len(self._graphs) >= self.max_graphs:
                 self._graphs.pop(next(iter(self._graphs)))
-            g = _ShapeGraph(self.model, B, N, self.dev)
+            g = _ShapeGraph(self.model, B, N, self.dev, self.with_words)
             self._graphs[(B, N)] = g
         return g
 
     @torch.inference_mode()
     def run(self, host_batches: Iterable[Tuple[Tensor, Tensor]]) -> Iterator[List[Tuple[str, List[int], List[int]]]]:
         """host_batches: iterable of (wav [B, N] float32 pinned host tensor, lengths [B] int64) -> hypotheses per batch."""
+        for host in self.run_raw(host_batches):
+            yield self.model.decoding.to_hypotheses(*host[:3])
+
+    @torch.inference_mode()
+    def run_raw(self, host_batches: Iterable[Tuple[Tensor, Tensor]]) -> Iterator[List[Tensor]]:
+        """Like `run`, but yields the pinned host copies of the device step's outputs: ids, frames, counts, encoded_len
+        (+ word_start, word_end, word_first, word_ntok, n_words with `with_words`)."""
         model = self.model
         compute = torch.cuda.current_stream(self.dev)
         it = iter(host_batches)
@@ -90,19 +110,18 @@ class BatchPipeline:
                 g.wav.copy_(wav_d, non_blocking=True)   # device-to-device refill of the graph's static input
                 g.len.copy_(len_d, non_blocking=True)
                 g.graph.replay()
-                ids, frames, counts = g.out
+                outs = g.out
             else:
-                enc, enc_len = model(wav_d, len_d)
-                ids, frames, counts = model.decoding.decode_device(model.head, enc, enc_len)
-            host = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in (ids, frames, counts)]
-            for h, t in zip(host, (ids, frames, counts)):
+                outs = device_step(model, wav_d, len_d, self.with_words)
+            host = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in outs]
+            for h, t in zip(host, outs):
                 h.copy_(t, non_blocking=True)           # stream-ordered before the next replay overwrites the outputs
             done = torch.cuda.Event()
             done.record(compute)
             if prev is not None:
                 prev[1].synchronize()
-                yield model.decoding.to_hypotheses(*prev[0])
+                yield prev[0]
             prev = (host, done)
         if prev is not None:
             prev[1].synchronize()
-            yield model.decoding.to_hypotheses(*prev[0])
+            yield prev[0]

@@ -777,6 +777,88 @@ def test_many_distinct_lengths_do_not_leak_workspaces(dev, v2_ctc_ckpt):
     assert max(peaks[12:]) <= max(peaks[:12]) * 1.5 + (64 << 20)
 
 
+def test_packed_weight_cache_and_triton_contract(dev, v2_ctc_ckpt, tmp_path):
+    """(a) a checkpoint FILE loads through `load_model(download_root=...)`; the second load finds the packed
+    weights cached next to it (keyed by the file's md5) and gives bit-identical results; (b) the Triton ensemble's I/O
+    contract (audio_batch FP32 concat + INT64 lengths -> texts) served by one call chain on the GPU."""
+    from gigaam_b200.serving.triton_backend import config_pbtxt, transcribe_concatenated
+    ck = synthetic.synthetic_checkpoint("v2_ctc", seed=0, n_layers=2)
+    torch.save(ck, tmp_path / "v2_ctc.ckpt")
+    m1 = gigaam.load_model("v2_ctc", device=dev, download_root=str(tmp_path))
+    wav, wav_len = synthetic.synthetic_audio(3, 2.0, seed=8, ragged=True)
+    e1, l1 = m1(wav.to(dev), wav_len.to(dev))
+    assert m1._get_engine().pack_cache_hit is False
+    assert len(list(tmp_path.glob("v2_ctc.*.float16.b200pack"))) == 1
+    m2 = gigaam.load_model("v2_ctc", device=dev, download_root=str(tmp_path))
+    e2, l2 = m2(wav.to(dev), wav_len.to(dev))
+    assert m2._get_engine().pack_cache_hit is True and torch.equal(e1, e2) and torch.equal(l1, l2)
+    # Triton contract: concatenated utterances in, one text per utterance out, in request order
+    lens = [int(n) for n in wav_len]
+    concat = np.concatenate([wav[i, : lens[i]].numpy() for i in range(3)])
+    texts = transcribe_concatenated(m2, concat, np.asarray(lens, dtype=np.int64), max_utterances=2)
+    alone = [str(m2.transcribe(wav[i, : lens[i]])) for i in range(3)]
+    assert texts[0] == alone[0] and len(texts) == 3 and all(isinstance(t, str) for t in texts)
+    assert [t[:-3] for t in texts] == [a[: len(t[:-3])] for t, a in zip(texts, alone)]    # padded members may differ in the tail
+    cfg = config_pbtxt(model_name="v2_ctc")
+    assert 'name: "audio_batch"' in cfg and "TYPE_INT64" in cfg and "TYPE_STRING" in cfg
+    with pytest.raises(ValueError):
+        transcribe_concatenated(m2, concat, [concat.size, 5])
+
+
+def test_transcribe_longform_against_oracle(dev):
+    """transcribe_longform (gigaam/model.py:195-259) over pre-cut segments against the ORACLE: every segment's text and word
+    timestamps must equal the CPU oracle's greedy decode of that segment (fp16-rounded waveform and encoder parameters, as
+    the reference does on CUDA), shifted by the segment start.  Segments were picked (2-layer synthetic model) so that the
+    oracle's top-2 logit margin stays above 0.02 on every frame -- asserted here, so the comparison can be exact."""
+    from gigaam_b200.longform import plan_batches
+    from gigaam_b200.timestamps_utils import frames_to_words
+    ck = synthetic.synthetic_checkpoint("v2_ctc", seed=0, n_layers=2)
+    model = gigaam.load_model("v2_ctc", device=dev, checkpoint=ck)
+    sd16, cfg = _fp16_rounded(ck["state_dict"]), ck["cfg"]
+    vocab = cfg["decoding"]["vocabulary"]
+    seeds = [203, 211, 217, 241, 249, 252, 212, 226, 250, 242]
+    segments = [synthetic.synthetic_audio(1, 2.0 + (sd % 5) * 0.7, seed=sd)[0][0] for sd in seeds]
+    bounds, t0 = [], 0.0
+    for s in segments:
+        bounds.append((t0, t0 + s.numel() / 16000.0))
+        t0 += s.numel() / 16000.0 + 0.25
+
+    def oracle(wav, wav_len):
+        with torch.inference_mode():
+            enc, enc_len = orc.model_forward(wav.half().float(), wav_len, sd16, cfg)
+        top2 = orc.ctc_logits(enc, sd16).topk(2, dim=-1).values
+        margin = top2[..., 0] - top2[..., 1]
+        ok = [float(margin[i, : int(enc_len[i])].min()) > 0.02 for i in range(wav.shape[0])]
+        return orc.ctc_greedy(enc, enc_len, sd16), enc_len, ok
+
+    # one segment per batch: no padding, exact for every segment
+    res = model.transcribe_longform(None, word_timestamps=True, fr_batch_size=1, segments=segments, boundaries=bounds)
+    assert len(res) == len(segments) and res.has_word_timestamps
+    for seg, wav, (s0, e0) in zip(res, segments, bounds):
+        hyp, enc_len, ok = oracle(wav[None], torch.tensor([wav.numel()]))
+        assert ok[0], "test segment lost its margin: pick another seed"
+        ids, frames = hyp[0]
+        assert seg.text == "".join(vocab[i] for i in ids) and (seg.start, seg.end) == (s0, e0)
+        want = frames_to_words(model.decoding.tokenizer, ids, frames, wav.numel() / 16000.0 / int(enc_len[0]))
+        assert [w.text for w in seg.words] == [w.text for w in want]
+        for a, b in zip(seg.words, want):
+            assert a.start == pytest.approx(b.start + s0, abs=2e-3) and a.end == pytest.approx(b.end + s0, abs=2e-3)
+    # length-bucketed batches of 4: the oracle runs the SAME padded batches (padding semantics are part of the path)
+    res4 = model.transcribe_longform(None, fr_batch_size=4, segments=segments, boundaries=bounds)
+    lengths = [s.numel() for s in segments]
+    compared = 0
+    for batch in plan_batches(lengths, 4):
+        wav = torch.zeros(len(batch), max(lengths[i] for i in batch))
+        for row, i in enumerate(batch):
+            wav[row, : lengths[i]] = segments[i]
+        hyp, _, ok = oracle(wav, torch.tensor([lengths[i] for i in batch]))
+        for row, i in enumerate(batch):
+            if ok[row]:
+                assert res4.segments[i].text == "".join(vocab[k] for k in hyp[row][0]), i
+                compared += 1
+    assert compared >= 5
+
+
 def test_transcribe_longform_equals_per_segment_transcribe(dev, v2_ctc_ckpt):
     """transcribe_longform (gigaam/model.py:195-259) over pre-cut segments == transcribe() of every segment alone, in
     recording order, with word timestamps shifted by the segment start; the built-in splitter handles a 50 s waveform
