@@ -179,6 +179,65 @@ def cpu_reference(steps: int, warmup: int, batch: int = 4, reps: int = 3, second
             "rtfx": batch * reps * seconds / sec, "sec_per_step": sec}
 
 
+def c4_strong_scaling(dev, rank: int, world: int, steps: int = 3, total: int = 256, chunk: int = 32, seconds: float = 10.0):
+    """BASELINE.json configs[3]: v3_e2e_rnnt, 256 x 10 s in total, sharded across the N GPUs of the job (STRONG scaling:
+    the work is fixed, 256 / N utterances per rank, run in device batches of 32 = the per-GPU batch at N = 8), encoder +
+    RNN-T greedy loop on every rank, then ONE packed all-gather of all hypotheses (gam_gather_hyps) inside the timed
+    region.  Device-timed with CUDA events, max over ranks.  Returns the dict reported under `strong_scaling_c4`."""
+    import torch
+    import torch.distributed as dist
+    import gigaam_b200 as gigaam
+    from gigaam_b200.dist import HypothesisGather, shard_bounds, unpack_gathered
+
+    model = gigaam.load_model("v3_e2e_rnnt", device=dev, synthetic=True)
+    eng = model._get_engine()
+    s0, s1 = shard_bounds(total, rank, world)
+    rows = (total + world - 1) // world
+    wav, wav_len = gigaam.synthetic_audio(s1 - s0, seconds, seed=1234 + rank)
+    wav, wav_len = wav.to(dev), wav_len.to(dev)
+    T = eng.encoded_frames(eng.logmel_frames(wav.shape[1]))
+    W = eng.hyp_width(T)
+    gather = HypothesisGather(eng) if world > 1 else None
+    packed = eng.packed_hypotheses(rows, T)
+    ids_v = packed[: rows * W].view(rows, W)
+    frames_v = packed[rows * W: 2 * rows * W].view(rows, W)
+    counts_v = packed[2 * rows * W:]
+
+    def step():
+        for c0 in range(0, s1 - s0, chunk):
+            c1 = min(c0 + chunk, s1 - s0)
+            enc, enc_len = model(wav[c0:c1], wav_len[c0:c1])
+            ids, frames, counts = model.decoding.decode_device(model.head, enc, enc_len)
+            ids_v[c0:c1], frames_v[c0:c1], counts_v[c0:c1] = ids, frames, counts
+        if gather is not None:
+            return unpack_gathered(gather.all_gather(packed), total, world, rows, W), enc_len
+        return (ids_v, frames_v, counts_v), enc_len
+
+    with torch.inference_mode():
+        for _ in range(2):
+            out, enc_len = step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            out, enc_len = step()
+        e1.record()
+        torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / steps
+    counts = out[2].cpu()
+    assert counts.numel() == total
+    return {"metric": "utterances/sec (v3_e2e_rnnt, 256 x 10 s in total, sharded over the job's GPUs)", "value": total / (ms * 1e-3),
+            "unit": "utt/s", "ms_per_step": ms, "steps": steps, "global_batch": total, "per_gpu_batch": s1 - s0, "device_batch": chunk,
+            "scaling": "strong", "gather_in_timed_region": world > 1,
+            "tokens_per_frame": float(counts.sum()) / float(total * T), "rtfx": total * seconds / (ms * 1e-3),
+            "api": "model(wav, len) + model.decoding.decode_device(...) per device batch, gam_gather_hyps once per step"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -187,6 +246,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-c4", action="store_true", help="skip the strong-scaling leg (BASELINE configs[3])")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -237,18 +297,22 @@ def main():
     T = eng.encoded_frames(M)
     mel_len = model.preprocessor.out_len(wav_len)
     static_in = torch.empty_like(wavs[0])
-    gathered = [torch.empty((world * B, T), dtype=torch.int32, device=dev), torch.empty((world * B,), dtype=torch.int32, device=dev)] if world > 1 else None
+    # the path's only exchange: every rank's packed hypotheses to every rank, ONE ncclAllGather issued by the
+    # library (gam_gather_hyps) on the compute stream -- inside the CUDA graph below, so replicas are not re-synchronised
+    # by host-side collectives between steps
+    hyp_gather = None
+    if world > 1:
+        from gigaam_b200.dist import HypothesisGather
+        hyp_gather = HypothesisGather(eng)
+    packed = eng.packed_hypotheses(B, T)
 
-    def device_step(wav):
+    def device_step(wav, collective=True):
         mel = eng.logmel(wav)
         enc, enc_len = eng.encode(mel, mel_len)
-        ids, frames, counts = eng.greedy(enc, enc_len)
-        return ids, frames, counts
-
-    def gather(ids, counts):
-        if world > 1:  # the path's only exchange: hypotheses to every rank over NVLink
-            dist.all_gather_into_tensor(gathered[0], ids)
-            dist.all_gather_into_tensor(gathered[1], counts)
+        ids, frames, counts = eng.greedy(enc, enc_len, packed)
+        if hyp_gather is not None and collective:
+            return ids, frames, counts, hyp_gather.all_gather(packed)
+        return ids, frames, counts, None
 
     # ---- warm-up eagerly, then capture the whole step in one CUDA graph (kills ~250 launch gaps)
     side = torch.cuda.Stream(device=dev)
@@ -262,12 +326,11 @@ def main():
     side.synchronize()
     graph = torch.cuda.CUDAGraph()
     with torch.cuda.graph(graph, stream=side):
-        g_ids, g_frames, g_counts = device_step(static_in)
+        g_ids, g_frames, g_counts, g_all = device_step(static_in)
 
     def graph_step(i):
         static_in.copy_(wavs[i % N_ROT], non_blocking=True)  # device->device refill of the static input (41 MB)
         graph.replay()
-        gather(g_ids, g_counts)
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -321,7 +384,7 @@ def main():
     # same calls, same per-step H2D / D2H, but driven by gigaam_b200.pipeline.BatchPipeline: the copy of step i+1 and the
     # read-back + detokenisation of step i-1 overlap the kernels of step i
     from gigaam_b200.pipeline import BatchPipeline
-    pipe = BatchPipeline(model)
+    pipe = BatchPipeline(model, gather=hyp_gather)      # N > 1: every rank ends up with the hypotheses of all ranks
     n_hyp = sum(len(h) for h in pipe.run((host_wavs[i % N_ROT], host_len) for i in range(3)))
     torch.cuda.synchronize()
     if world > 1:
@@ -330,14 +393,14 @@ def main():
     n_hyp = sum(len(h) for h in pipe.run((host_wavs[i % N_ROT], host_len) for i in range(args.steps)))
     torch.cuda.synchronize()
     e2e_sec = time.perf_counter() - t0
-    assert n_hyp == B * args.steps
+    assert n_hyp == world * B * args.steps
     t = torch.tensor([e2e_sec, e2e_serial_sec], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * B * args.steps / float(t[0].item())
     e2e_serial_value = world * B * args.steps / float(t[1].item())
     h2d = B * n_samples * 4 + B * 8
-    d2h = 2 * B * T * 4 + 2 * B * 4      # ids, frames [B, T'] + counts, encoded_len [B], int32
+    d2h = world * (2 * B * T * 4 + B * 4) + B * 4     # ids, frames [B, T'] + counts of every rank's batch, encoded_len [B]; int32
 
     # ---- dominant kernel, timed live with CUDA events on the launching stream
     roofline = None
@@ -351,7 +414,7 @@ def main():
         eng.profile_begin()
         nprof = 3
         for i in range(nprof):
-            device_step(wavs[i % N_ROT])
+            device_step(wavs[i % N_ROT], collective=False)     # rank 0 only: the kernels without the all-gather
         prof = eng.profile_end()
         fl = flops_per_utterance(n_samples)
         R = B * fl["T"]
@@ -376,6 +439,8 @@ def main():
                     "step_frac": B * fl["total"] / (ms_per_step * 1e-3) / 1e12 / peak_tf,
                     "classes_ms_per_step": {k: round(v[0] / nprof, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}}
 
+    del pipe, graph
+    strong = None if args.no_c4 else c4_strong_scaling(dev, rank, world)
     if rank == 0:
         # the CPU baseline is a property of the box, not of N: timed at N = 1 only (other ranks would idle behind it)
         cpu = None if (args.no_cpu_baseline or world > 1) else cpu_reference(steps=4, warmup=1)   # ~12 s of CPU work
@@ -389,7 +454,7 @@ def main():
                                "hypotheses out, copies of neighbouring steps overlapped with compute, kernels replayed as one CUDA graph per shape",
                         "serial_value": e2e_serial_value},
                 "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
-                "roofline": roofline,
+                "roofline": roofline, "strong_scaling_c4": strong,
                 "cpu_baseline": ({k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")} if cpu else None)}
         real_stdout.write(json.dumps(line) + "\n")
         real_stdout.flush()

@@ -20,12 +20,12 @@ int launch_v2(const CUtensorMap* ta, const CUtensorMap* tw, GemmParams p, int nu
   const int max_pairs = num_sms / 2;
   const int npairs = tiles < max_pairs ? tiles : max_pairs;
   if (npairs <= 0) return 0;
-  return launch_k(kern, dim3(2 * npairs), dim3(kG2Threads), kG2Smem, s, *ta, ta2 ? *ta2 : *ta, *tw, p) == cudaSuccess ? 0 : -2;
+  return launch_k(kern, dim3(2 * npairs), dim3(G2Cfg<EPI>::kThreads), G2Cfg<EPI>::kSmem, s, *ta, ta2 ? *ta2 : *ta, *tw, p) == cudaSuccess ? 0 : -2;
 }
 
 template <int EPI, int AMODE>
 int set_attr() {
-  return cudaFuncSetAttribute(gemm2_f16_tn_kernel<EPI, AMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kG2Smem) == cudaSuccess ? 0 : -1;
+  return cudaFuncSetAttribute(gemm2_f16_tn_kernel<EPI, AMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2Cfg<EPI>::kSmem) == cudaSuccess ? 0 : -1;
 }
 
 }  // namespace

@@ -47,13 +47,15 @@ class _GreedyBase:
         self.tokenizer = Tokenizer(vocabulary, model_path)
         self.blank_id = len(self.tokenizer)
 
-    def decode_device(self, head, encoded: Tensor, lengths: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
-        """Device-resident result: ids [B, max_out] i32, frames [B, max_out] i32, counts [B] i32."""
+    def decode_device(self, head, encoded: Tensor, lengths: Tensor, packed: Optional[Tensor] = None
+                      ) -> Tuple[Tensor, Tensor, Tensor]:
+        """Device-resident result: ids [B, max_out] i32, frames [B, max_out] i32, counts [B] i32 (views of `packed`, an
+        `Engine.packed_hypotheses` buffer, when one is given: the layout the multi-GPU gather ships)."""
         eng = head._engine()
         assert eng.num_classes == len(self.tokenizer) + 1, \
             f"Num classes {eng.num_classes} != len(vocab)+1 {len(self.tokenizer) + 1}"
         enc = _as_btd(encoded.to(device=eng.device, dtype=torch.float32))
-        return eng.greedy(enc, lengths)
+        return eng.greedy(enc, lengths, packed)
 
     @torch.inference_mode()
     def decode(self, head, encoded: Tensor, lengths: Tensor) -> List[Tuple[str, List[int], List[int]]]:

@@ -53,6 +53,8 @@ def unpack_gathered(gathered: Tensor, batch: int, world: int, rows: int, width: 
     ids = g[:, : rows * width].reshape(world, rows, width)
     frames = g[:, rows * width: 2 * rows * width].reshape(world, rows, width)
     counts = g[:, 2 * rows * width:].reshape(world, rows)
+    if batch == world * rows:        # even split: pure reshapes (no host-built index: capturable in a CUDA graph)
+        return ids.reshape(batch, width), frames.reshape(batch, width), counts.reshape(batch)
     keep = torch.cat([torch.arange(r * rows, r * rows + (shard_bounds(batch, r, world)[1] - shard_bounds(batch, r, world)[0]))
                       for r in range(world)]).to(g.device)
     return (ids.reshape(world * rows, width)[keep].contiguous(), frames.reshape(world * rows, width)[keep].contiguous(),
@@ -121,6 +123,10 @@ def transcribe_sharded(model, wav: Tensor, lengths: Tensor, gather: Optional[Hyp
     width = T if eng.head_type == 1 else T * eng.max_symbols
     ids = frames = counts = None
     if w.shape[0] > 0:
+        if w.shape[0] == 1:
+            # a lone utterance gets no attention mask (gigaam/encoder.py:616-626: masks exist only for B > 1), so its padding
+            # must not reach the encoder: trim it, as a caller of the unsharded reference would never pad a batch of one
+            w = w[:, : int(l[0])]
         enc, enc_len = model(w.to(dev), l.to(dev))
         ids, frames, counts = model.decoding.decode_device(model.head, enc, enc_len)
     if gather is None and world > 1 and dev.type == "cuda" and dist.get_backend() == "nccl":

@@ -428,17 +428,34 @@ class Engine:
         _lib.check(self.lib, self.handle, rc, "gam_encode")
         return enc, enc_len
 
-    def greedy(self, enc_btd: Tensor, enc_len: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
-        """enc [B, T, d] f32 contiguous, len [B] -> (ids [B, max_out] i32, frames, counts [B] i32) on device."""
+    def hyp_width(self, T: int) -> int:
+        """Row pitch of the id / frame matrices for T encoder frames."""
+        return T if self.head_type == 1 else T * self.max_symbols
+
+    def packed_hypotheses(self, rows: int, T: int) -> Tensor:
+        """Zeroed int32 buffer [ids rows x W | frames rows x W | counts rows] (the layout gam_gather_hyps all-gathers)."""
+        w = self.hyp_width(T)
+        return torch.zeros(2 * rows * w + rows, dtype=torch.int32, device=self.device)
+
+    def greedy(self, enc_btd: Tensor, enc_len: Tensor, packed: Optional[Tensor] = None) -> Tuple[Tensor, Tensor, Tensor]:
+        """enc [B, T, d] f32 contiguous, len [B] -> (ids [B, max_out] i32, frames, counts [B] i32) on device.
+        `packed` (from packed_hypotheses, rows >= B): the results are written into that buffer and returned as views of it."""
         assert enc_btd.is_cuda and enc_btd.dtype == torch.float32 and enc_btd.is_contiguous()
         if self.head_type == 0:
             raise RuntimeError("model has no head to decode with")
         B, T, _ = enc_btd.shape
         enc_len = enc_len.to(device=self.device, dtype=torch.int32).contiguous()
-        max_out = T if self.head_type == 1 else T * self.max_symbols
-        ids = torch.empty((B, max_out), dtype=torch.int32, device=self.device)
-        frames = torch.empty((B, max_out), dtype=torch.int32, device=self.device)
-        counts = torch.empty((B,), dtype=torch.int32, device=self.device)
+        max_out = self.hyp_width(T)
+        if packed is not None:
+            rows = packed.numel() // (2 * max_out + 1)
+            assert rows >= B and packed.numel() == rows * (2 * max_out + 1) and packed.dtype == torch.int32
+            ids = packed[: rows * max_out].view(rows, max_out)[:B]
+            frames = packed[rows * max_out: 2 * rows * max_out].view(rows, max_out)[:B]
+            counts = packed[2 * rows * max_out: 2 * rows * max_out + B]
+        else:
+            ids = torch.empty((B, max_out), dtype=torch.int32, device=self.device)
+            frames = torch.empty((B, max_out), dtype=torch.int32, device=self.device)
+            counts = torch.empty((B,), dtype=torch.int32, device=self.device)
         ws = self._ws_dec.get((B, T), int(self.lib.gam_decode_workspace_bytes(self.handle, B, T)), self.device)
         fn = self.lib.gam_ctc_greedy if self.head_type == 1 else self.lib.gam_rnnt_greedy
         with torch.cuda.device(self.device):

@@ -16,8 +16,9 @@ Tensor = torch.Tensor
 class _ShapeGraph:
     """The whole device step for one (B, N) input shape, captured once: static inputs -> static outputs."""
 
-    def __init__(self, model, B: int, N: int, dev: torch.device, with_words: bool = False):
+    def __init__(self, model, B: int, N: int, dev: torch.device, with_words: bool = False, gather=None):
         self.with_words = with_words
+        self.gather = gather
         self.wav = torch.zeros((B, N), dtype=torch.float32, device=dev)
         self.len = torch.full((B,), N, dtype=torch.int64, device=dev)
         side = torch.cuda.Stream(device=dev)
@@ -35,12 +36,22 @@ class _ShapeGraph:
         self._held = model._get_engine().held_workspaces(B, N)
 
     def _step(self, model):
-        return device_step(model, self.wav, self.len, self.with_words)
+        return device_step(model, self.wav, self.len, self.with_words, self.gather)
 
 
-def device_step(model, wav: Tensor, lengths: Tensor, with_words: bool = False):
-    """wav -> device-resident hypotheses (ids, frames, counts, encoded_len[, word records]): the kernels of one batch."""
+def device_step(model, wav: Tensor, lengths: Tensor, with_words: bool = False, gather=None):
+    """wav -> device-resident hypotheses (ids, frames, counts, encoded_len[, word records]): the kernels of one batch.
+    With `gather` (dist.HypothesisGather; every rank runs the same number of equally shaped steps) the shard's packed
+    hypotheses are all-gathered inside the step and ids / frames / counts are those of the GLOBAL batch."""
     enc, enc_len = model(wav, lengths)
+    if gather is not None:
+        from .dist import unpack_gathered
+        eng = model._get_engine()
+        B, T = enc.shape[0], enc.shape[2]
+        packed = eng.packed_hypotheses(B, T)
+        model.decoding.decode_device(model.head, enc, enc_len, packed)
+        ids, frames, counts = unpack_gathered(gather.all_gather(packed), B * gather.world, gather.world, B, eng.hyp_width(T))
+        return ids, frames, counts, enc_len
     ids, frames, counts = model.decoding.decode_device(model.head, enc, enc_len)
     if not with_words:
         return ids, frames, counts, enc_len
@@ -51,9 +62,10 @@ class BatchPipeline:
     """`run(host_batches)` yields the hypotheses of every batch.  `with_words=True` also groups tokens into words on the
     device (csrc/words.cu) and `run_raw` then yields the host copies of the raw records for word timestamps."""
 
-    def __init__(self, model, use_graph: bool = True, max_graphs: int = 4, with_words: bool = False):
+    def __init__(self, model, use_graph: bool = True, max_graphs: int = 4, with_words: bool = False, gather=None):
         self.model = model
         self.with_words = with_words
+        self.gather = gather          # dist.HypothesisGather: results are then those of all ranks' batches
         self.dev = model._device
         self.copy_stream = torch.cuda.Stream(device=self.dev)
         self.use_graph = use_graph
@@ -74,7 +86,7 @@ class BatchPipeline:
         if g is None:
             if len(self._graphs) >= self.max_graphs:
                 self._graphs.pop(next(iter(self._graphs)))
-            g = _ShapeGraph(self.model, B, N, self.dev, self.with_words)
+            g = _ShapeGraph(self.model, B, N, self.dev, self.with_words, self.gather)
             self._graphs[(B, N)] = g
         return g
 
@@ -112,7 +124,7 @@ class BatchPipeline:
                 g.graph.replay()
                 outs = g.out
             else:
-                outs = device_step(model, wav_d, len_d, self.with_words)
+                outs = device_step(model, wav_d, len_d, self.with_words, self.gather)
             host = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in outs]
             for h, t in zip(host, outs):
                 h.copy_(t, non_blocking=True)           # stream-ordered before the next replay overwrites the outputs
