@@ -583,7 +583,7 @@ int gam_encode(gam_handle* h, const float* mel, const int64_t* mel_len, int32_t 
       rc |= launch_gemm_res_ln(&p->m_hid, &m.ff2_w2, R, c.d_ff, w.ff2_b2, p->x, p->x, 0.5f,
                                ln_fuse(l, 3, 3, w.ln_out_g, w.ln_out_b, last ? nullptr : h->layers[l + 1].ln_ff1_g,
                                        last ? nullptr : h->layers[l + 1].ln_ff1_b, last ? enc : p->x), nsm, s); }
-    if (rc) return fail(h, -4, "layer %d: a launch was rejected (rc=%d)", l, rc);
+    if (rc) return fail(h, -4, "layer %d: a launch was rejected (rc=%d): %s", l, rc, cudaGetErrorString(cudaGetLastError()));
   }
   cudaMemcpyAsync(enc_len, p->len2, B * sizeof(int), cudaMemcpyDeviceToDevice, s);
   GAM_CHECK_LAUNCH(h, "encode");
@@ -715,7 +715,7 @@ int gam_test_gemm(gam_handle* h, int32_t kind, const void* A, const void* W, con
     PROF(PC_MISC);
     rc = launch_gemm(kind, &ta, &tw, M, N, K, bias, res, out, ldo, scale, h->num_sms, s);
   }
-  if (rc) return fail(h, -4, "gemm launch rejected (rc=%d)", rc);
+  if (rc) return fail(h, -4, "gemm launch rejected (rc=%d): %s", rc, cudaGetErrorString(cudaGetLastError()));
   GAM_CHECK_LAUNCH(h, "test_gemm");
   return 0;
 }
@@ -754,7 +754,7 @@ int gam_test_gemm_ln(gam_handle* h, int32_t mode, const void* A, const void* W, 
     PROF(PC_MISC);
     rc = launch_gemm_res_ln(&ta, &tw, M, K, bias, x, x, scale, f, h->num_sms, s);
   }
-  if (rc) return fail(h, -4, "gemm_res_ln launch rejected (rc=%d)", rc);
+  if (rc) return fail(h, -4, "gemm_res_ln launch rejected (rc=%d): %s", rc, cudaGetErrorString(cudaGetLastError()));
   GAM_CHECK_LAUNCH(h, "test_gemm_ln");
   return 0;
 }

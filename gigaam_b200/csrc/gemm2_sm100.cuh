@@ -353,11 +353,13 @@ gemm2_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
 
-  // two sets: re-split the register file inside each role's own branch (ptxas sizes the code that follows a setmaxnreg
-  // within the branch; all four warps of warpgroup 0 have to execute the .dec)
-  if (warp_idx == 0) {
+  // Two sets: the register file is re-split per WARPGROUP -- all four warps of a warpgroup execute the SAME setmaxnreg
+  // instruction (one .dec for warpgroup 0, one .inc for the epilogue warpgroups), each at the top of its own branch,
+  // which is also what lets ptxas size the code of that branch for the new limit.
+  if (warp_idx < G2Cfg<EPI>::kEpiWarp0) {
+   if constexpr (kSets == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+   if (warp_idx == 0) {
     // ===================================================== TMA producer (both CTAs)
-    if constexpr (kSets == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
     if (ptx::elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
@@ -400,9 +402,8 @@ gemm2_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
       }
     }
-  } else if (warp_idx == 1) {
+   } else if (warp_idx == 1) {
     // ===================================================== MMA issuer (leader CTA only)
-    if constexpr (kSets == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
     if (leader) {
       int stage = 0;
       uint32_t phase = 0;
@@ -433,8 +434,7 @@ gemm2_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
-  } else if (warp_idx < G2Cfg<EPI>::kEpiWarp0) {
-    if constexpr (kSets == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");   // idle warps 2, 3 of warpgroup 0
+   }   // (two sets: warps 2 and 3 of warpgroup 0 have no role)
   } else {
     // ===================================================== epilogue (warps 2..9, or 4..19 with two sets; both CTAs)
     if constexpr (kSets == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");

@@ -165,10 +165,12 @@ class GigaAMASR(GigaAM):
 
     def _word_flags(self) -> Tensor:
         """Per-token flag table of the device word grouping (timestamps_utils.token_flag_table), built once."""
-        if self.__dict__.get("_token_flags") is None:
+        flags = self.__dict__.get("_token_flags")
+        if flags is None or flags.device != self._device:        # device-resident: the grouping runs inside CUDA graphs
             from .timestamps_utils import token_flag_table
-            self.__dict__["_token_flags"] = token_flag_table(self.decoding.tokenizer)
-        return self.__dict__["_token_flags"]
+            flags = token_flag_table(self.decoding.tokenizer).to(self._device)
+            self.__dict__["_token_flags"] = flags
+        return flags
 
     def _words_from_records(self, ids: Tensor, counts: Tensor, encoded_len: Tensor, wav_lens: Tensor, rec: List[Tensor]
                             ) -> List[Tuple[str, Optional[List[Word]]]]:

@@ -11,6 +11,7 @@ sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 import torch  # noqa: E402
 
 import gigaam_b200 as gigaam  # noqa: E402
+from bench import ClockSampler  # noqa: E402  (nvidia-smi clocks / throttle reasons during the timed region)
 
 CONFIGS = {
     "c1": ("v2_ctc", 1, 5.0), "c2": ("v2_ctc", 64, 10.0), "c3": ("v2_rnnt", 32, 15.0),
@@ -36,22 +37,29 @@ def run(name):
             return model.decoding.decode_device(model.head, enc, enc_len)
         return enc, enc_len
 
+    import time
     for _ in range(3):
         out = step()
     torch.cuda.synchronize()
-    n = 5
+    n = max(5, int(400.0 / max(1.0, B * sec / 50.0)))          # ~0.4 s of device time: enough nvidia-smi samples
+    sampler = ClockSampler(0)
+    sampler.start()
+    time.sleep(0.25)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
     e0.record()
     for _ in range(n):
         out = step()
     e1.record()
     torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    clocks = sampler.stop(t0, t1)
     ms = e0.elapsed_time(e1) / n
     eng.profile_begin()
     step()
     prof = eng.profile_end()
     res = {"config": name, "model": model_name, "batch": B, "seconds": sec, "ms_per_batch": round(ms, 3),
-           "utt_per_s": round(B / ms * 1e3, 1), "rtfx": round(B * sec / ms * 1e3),
+           "utt_per_s": round(B / ms * 1e3, 1), "rtfx": round(B * sec / ms * 1e3), "steps": n, "clocks": clocks,
            "classes_ms": {k: round(v[0], 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}}
     if has_head:
         counts = out[2]
