@@ -36,7 +36,7 @@ constexpr int kG2BarBytes = 256;
 // TWO epilogue sets: set s drains accumulator s, i.e. the tiles of local parity s, so two tiles are in their epilogue at
 // once and the bytes in flight per SM double.  Cost: a 4-stage operand ring, and 20 warps (warpgroup 0 = producer, MMA
 // issuer and two idle warps; warpgroups 1-4 = the two sets) whose register file is re-split with setmaxnreg: 24 per
-// thread for warpgroup 0, 120 for the epilogue warpgroups.
+// thread for warpgroup 0, 112 for the epilogue warpgroups (the .inc draws on the CTA pool the .dec fills: 128 x 72 released >= 512 x 16 claimed).
 template <int EPI>
 struct G2Cfg {
   static constexpr int kSets = (EPI == EPI_BIAS_RES_F32 || EPI == EPI_BIAS_RES_LN_F32) ? 2 : 1;
@@ -437,7 +437,7 @@ gemm2_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
    }   // (two sets: warps 2 and 3 of warpgroup 0 have no role)
   } else {
     // ===================================================== epilogue (warps 2..9, or 4..19 with two sets; both CTAs)
-    if constexpr (kSets == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");
+    if constexpr (kSets == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
     const int quad = warp_idx & 3;          // TMEM lane quadrant
     const int lane = threadIdx.x & 31;
     const int ewg = warp_idx - G2Cfg<EPI>::kEpiWarp0;   // epilogue warp index over all sets: owns one staging tile
@@ -498,7 +498,7 @@ gemm2_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       constexpr bool kLn = EPI == EPI_BIAS_RES_LN_F32;
       [[maybe_unused]] const int c4 = (lane & 7) * 4;
       if constexpr (kRes) {
-        // ---- fp32 residual epilogue (two sets, 120 registers): x = res + scale * (acc + bias), residual of the next
+        // ---- fp32 residual epilogue (two sets, 112 registers): x = res + scale * (acc + bias), residual of the next
         // 32-column chunk in flight while this one is transposed and stored; accumulator read 16 columns at a time
         float* outp = reinterpret_cast<float*>(p.out);
         float4 rr[2][8];
