@@ -51,7 +51,7 @@ EXPORTS = ("gam_create", "gam_destroy", "gam_last_error", "gam_version", "gam_lo
            "gam_workspace_bytes", "gam_logmel", "gam_encode", "gam_ctc_greedy", "gam_rnnt_greedy", "gam_test_gemm",
            "gam_test_attention", "gam_launch_count", "gam_profile_begin", "gam_profile_end", "gam_profile_class_count",
            "gam_profile_class_name", "gam_logmel_workspace_bytes", "gam_logmel_tc", "gam_test_attention_relpos",
-           "gam_decode_workspace_bytes", "gam_test_gemm_ln", "gam_group_words", "gam_comm_unique_id", "gam_comm_init",
+           "gam_decode_workspace_bytes", "gam_group_words", "gam_comm_unique_id", "gam_comm_init",
            "gam_comm_nccl_version", "gam_gather_hyps")
 
 
@@ -88,8 +88,6 @@ def load() -> C.CDLL:
     lib.gam_workspace_bytes.restype = i64
     lib.gam_decode_workspace_bytes.argtypes = [H, i32, i32]
     lib.gam_decode_workspace_bytes.restype = i64
-    lib.gam_test_gemm_ln.argtypes = [H, i32] + [c_vp] * 11 + [i32, i32, i32, C.c_float, c_vp, i64, c_vp]
-    lib.gam_test_gemm_ln.restype = C.c_int
     lib.gam_comm_unique_id.argtypes = [c_vp]
     lib.gam_comm_unique_id.restype = C.c_int
     lib.gam_comm_init.argtypes = [H, c_vp, i32, i32]

@@ -95,12 +95,6 @@ struct Plan {
   __half* melT = nullptr;   // conv1d subsampling: time-major fp16 copy of the log-mel
   CUtensorMap m_melT, m_s1_3d;
   float* x = nullptr;
-  // fused LayerNorm exchange (gemm_params.cuh: LnFuse): two rounds of per-row partial statistics, and one zero-initialised
-  // arrival counter set per fused GEMM launch of the layer stack (4 per layer x 2 rounds)
-  float2 *ln_stats = nullptr, *ln_stats2 = nullptr;
-  unsigned int* ln_cnt = nullptr;
-  int ln_groups = 0;          // 32-row groups covered by one counter set
-  int64_t ln_cnt_bytes = 0;
   int64_t bytes = 0;
   CUtensorMap m_s1, m_s2, m_a16, m_r16, m_hid, m_qkv, m_qkv4, m_o16;
 };
@@ -205,11 +199,6 @@ int64_t plan_carve(const gam_handle* h, Plan* p, uint8_t* base) {
   p->len1 = reinterpret_cast<int*>(take(B * 4));
   p->len2 = reinterpret_cast<int*>(take(B * 4));
   p->x = reinterpret_cast<float*>(take(R * d * 4));
-  p->ln_stats = reinterpret_cast<float2*>(take(R * 6 * 8));
-  p->ln_stats2 = reinterpret_cast<float2*>(take(R * 6 * 8));
-  p->ln_groups = static_cast<int>((R + 255) / 256 * 8);
-  p->ln_cnt_bytes = static_cast<int64_t>(c.n_layers) * 4 * 2 * p->ln_groups * 4;
-  p->ln_cnt = reinterpret_cast<unsigned int*>(take(p->ln_cnt_bytes));
   p->a16 = reinterpret_cast<__half*>(take(R * d * 2));
   p->r16 = reinterpret_cast<__half*>(take(R * d * 2));
   p->big16 = reinterpret_cast<__half*>(take(R * wide * 2));
@@ -501,44 +490,22 @@ int gam_encode(gam_handle* h, const float* mel, const int64_t* mel_len, int32_t 
     if (rc) return fail(h, -4, "conv1d subsampling launch rejected (rc=%d)", rc);
   }
   if (L > 0) {
-    { PROF(PC_LAYERNORM);
-      launch_ln_f16(p->x, h->layers[0].ln_ff1_g, h->layers[0].ln_ff1_b, p->a16, R, s); }
-    { PROF(PC_MISC);
-      cudaMemsetAsync(p->ln_cnt, 0, static_cast<size_t>(p->ln_cnt_bytes), s); }
+    PROF(PC_LAYERNORM);
+    launch_ln_f16(p->x, h->layers[0].ln_ff1_g, h->layers[0].ln_ff1_b, p->a16, R, s);
   }
   const int dk = d / c.n_heads;
-  // every residual GEMM of the stack carries the LayerNorm(s) that follow it (LnFuse): launch `slot` of layer `l` owns
-  // counter sets 2 * (4 l + slot) and + 1
-  auto ln_fuse = [&](int l, int slot, int mode, const float* g, const float* b, const float* g2, const float* b2, float* xout) {
-    LnFuse f{};
-    f.mode = mode;
-    f.g = g; f.b = b; f.g2 = g2; f.b2 = b2;
-    f.out16 = p->a16;
-    f.rope16 = p->r16;
-    f.xout = xout;
-    f.stats = p->ln_stats;
-    f.stats2 = p->ln_stats2;
-    f.cnt = p->ln_cnt + static_cast<size_t>(2 * (4 * l + slot)) * p->ln_groups;
-    f.cnt2 = f.cnt + p->ln_groups;
-    f.rope_cos = h->w.rope_cos;
-    f.rope_sin = h->w.rope_sin;
-    f.T = p->T2;
-    f.half_dim = dk / 2;
-    f.eps = 1e-5f;
-    return f;
-  };
   for (int l = 0; l < L; ++l) {
     const gam_layer_weights& w = h->layers[l];
     const LayerMaps& m = h->lmaps[l];
-    const bool rotary = c.self_attention == 0;
-    // x += 0.5 * FF1(LN(x)) ; then u = norm_self_att(x) (+ rope(u))           (encoder.py:480-487, 245-250)
+    // x += 0.5 * FF1(LN(x))                                     (encoder.py:480-483)
     { PROF(PC_GEMM_FFN_UP);
       rc |= launch_gemm(GEMM_BIAS_SILU_F16, &p->m_a16, &m.ff1_w1, R, c.d_ff, d, w.ff1_b1, nullptr, p->big16, c.d_ff, 1.f, nsm, s); }
     { PROF(PC_GEMM_FFN_DOWN);
-      rc |= launch_gemm_res_ln(&p->m_hid, &m.ff1_w2, R, c.d_ff, w.ff1_b2, p->x, p->x, 0.5f,
-                               ln_fuse(l, 0, rotary ? 2 : 1, w.ln_att_g, w.ln_att_b, nullptr, nullptr, nullptr), nsm, s); }
-    // x += W_o attn(q = W_q rope(u), k = W_k rope(u), v = W_v u)               (encoder.py:236-277)
-    if (rotary) {
+      rc |= launch_gemm(GEMM_BIAS_RES_F32, &p->m_hid, &m.ff1_w2, R, d, c.d_ff, w.ff1_b2, p->x, p->x, d, 0.5f, nsm, s); }
+    // x += W_o attn(q = W_q rope(u), k = W_k rope(u), v = W_v u), u = LN(x)   (encoder.py:485-487, 236-277)
+    if (c.self_attention == 0) {
+      { PROF(PC_LAYERNORM);
+        launch_ln_rope_f16(p->x, w.ln_att_g, w.ln_att_b, h->w.rope_cos, h->w.rope_sin, p->a16, p->r16, R, p->T2, dk / 2, s); }
       bool merged = false;
       if (m.qkv_merged) {
         PROF(PC_GEMM_QKV);
@@ -554,16 +521,18 @@ int gam_encode(gam_handle* h, const float* mel, const int64_t* mel_len, int32_t 
         rc |= launch_attention(&p->m_qkv, B > 1 ? p->len2 : nullptr, p->o16, B, p->T2, c.n_heads, dk, d, nsm, s); }
     } else {
       // rel_pos (encoder.py:208-228): one projection GEMM -> [q+u | q+v | k | v], position scores inside the kernel
+      { PROF(PC_LAYERNORM);
+        launch_ln_f16(p->x, w.ln_att_g, w.ln_att_b, p->a16, R, s); }
       { PROF(PC_GEMM_QKV);
         rc |= launch_gemm(GEMM_BIAS_F16, &p->m_a16, &m.w_qkv_rel, R, 4 * d, d, w.b_qkv_rel, nullptr, p->big16, 4 * d, 1.f, nsm, s); }
       { PROF(PC_ATTENTION);
         rc |= launch_attention_relpos(&p->m_qkv4, &m.pos_proj, B > 1 ? p->len2 : nullptr, p->o16, B, p->T2, c.n_heads, dk, d, s); }
     }
-    // attention output projection + residual ; then norm_conv                   (encoder.py:487-490)
     { PROF(PC_GEMM_PROJ);
-      rc |= launch_gemm_res_ln(&p->m_o16, &m.w_o, R, d, w.b_o, p->x, p->x, 1.f,
-                               ln_fuse(l, 1, 1, w.ln_conv_g, w.ln_conv_b, nullptr, nullptr, nullptr), nsm, s); }
-    // x += Conv(LN(x))                                                          (encoder.py:489-491, 396-409)
+      rc |= launch_gemm(GEMM_BIAS_RES_F32, &p->m_o16, &m.w_o, R, d, d, w.b_o, p->x, p->x, d, 1.f, nsm, s); }
+    // x += Conv(LN(x))                                           (encoder.py:489-491, 396-409)
+    { PROF(PC_LAYERNORM);
+      launch_ln_f16(p->x, w.ln_conv_g, w.ln_conv_b, p->a16, R, s); }
     { PROF(PC_GEMM_GLU);
       rc |= launch_gemm(GEMM_BIAS_GLU_F16, &p->m_a16, &m.pw1, R, 2 * d, d, w.pw1_b, nullptr, p->g16, d, 1.f, nsm, s); }
     { PROF(PC_DWCONV);
@@ -571,18 +540,21 @@ int gam_encode(gam_handle* h, const float* mel, const int64_t* mel_len, int32_t 
         rc |= launch_dwconv_bn_silu(p->g16, w.dw_w, w.dw_b, p->len2, p->o16, B, p->T2, c.conv_kernel_size, s);
       else
         rc |= launch_dwconv_ln_silu(p->g16, w.dw_w, w.dw_b, w.cn_g, w.cn_b, p->len2, p->o16, B, p->T2, c.conv_kernel_size, s); }
-    // pointwise_conv2 + residual ; then norm_feed_forward2
     { PROF(PC_GEMM_PROJ);
-      rc |= launch_gemm_res_ln(&p->m_o16, &m.pw2, R, d, w.pw2_b, p->x, p->x, 1.f,
-                               ln_fuse(l, 2, 1, w.ln_ff2_g, w.ln_ff2_b, nullptr, nullptr, nullptr), nsm, s); }
-    // x += 0.5 * FF2(LN(x)) ; x = norm_out(x) ; a16 = next layer's norm_feed_forward1(x)      (encoder.py:493-497, :481)
+      rc |= launch_gemm(GEMM_BIAS_RES_F32, &p->m_o16, &m.pw2, R, d, d, w.pw2_b, p->x, p->x, d, 1.f, nsm, s); }
+    // x += 0.5 * FF2(LN(x))                                      (encoder.py:493-495)
+    { PROF(PC_LAYERNORM);
+      launch_ln_f16(p->x, w.ln_ff2_g, w.ln_ff2_b, p->a16, R, s); }
     { PROF(PC_GEMM_FFN_UP);
       rc |= launch_gemm(GEMM_BIAS_SILU_F16, &p->m_a16, &m.ff2_w1, R, c.d_ff, d, w.ff2_b1, nullptr, p->big16, c.d_ff, 1.f, nsm, s); }
     { PROF(PC_GEMM_FFN_DOWN);
-      const bool last = l + 1 == L;
-      rc |= launch_gemm_res_ln(&p->m_hid, &m.ff2_w2, R, c.d_ff, w.ff2_b2, p->x, p->x, 0.5f,
-                               ln_fuse(l, 3, 3, w.ln_out_g, w.ln_out_b, last ? nullptr : h->layers[l + 1].ln_ff1_g,
-                                       last ? nullptr : h->layers[l + 1].ln_ff1_b, last ? enc : p->x), nsm, s); }
+      rc |= launch_gemm(GEMM_BIAS_RES_F32, &p->m_hid, &m.ff2_w2, R, d, c.d_ff, w.ff2_b2, p->x, p->x, d, 0.5f, nsm, s); }
+    // x = LN_out(x) (+ next layer's first LN fused)                (encoder.py:497)
+    { PROF(PC_LAYERNORM);
+      if (l + 1 < L)
+        launch_ln_out_ln(p->x, w.ln_out_g, w.ln_out_b, h->layers[l + 1].ln_ff1_g, h->layers[l + 1].ln_ff1_b, p->x, p->a16, R, s);
+      else
+        launch_ln_out_ln(p->x, w.ln_out_g, w.ln_out_b, nullptr, nullptr, enc, nullptr, R, s); }
     if (rc) return fail(h, -4, "layer %d: a launch was rejected (rc=%d): %s", l, rc, cudaGetErrorString(cudaGetLastError()));
   }
   cudaMemcpyAsync(enc_len, p->len2, B * sizeof(int), cudaMemcpyDeviceToDevice, s);
@@ -717,45 +689,6 @@ int gam_test_gemm(gam_handle* h, int32_t kind, const void* A, const void* W, con
   }
   if (rc) return fail(h, -4, "gemm launch rejected (rc=%d): %s", rc, cudaGetErrorString(cudaGetLastError()));
   GAM_CHECK_LAUNCH(h, "test_gemm");
-  return 0;
-}
-
-int gam_test_gemm_ln(gam_handle* h, int32_t mode, const void* A, const void* W, const float* bias, float* x, const float* g,
-                     const float* b, const float* g2, const float* b2, void* out16, void* rope16, float* xout, int32_t M, int32_t K,
-                     int32_t T, float scale, void* workspace, int64_t workspace_bytes, void* stream) {
-  const gam_config& c = h->cfg;
-  CUtensorMap ta, tw;
-  int rc = make_tmap_2d_f16(&ta, A, M, K, K, 128, 64);
-  rc |= make_tmap_2d_f16(&tw, W, c.d_model, K, K, 128, 64);
-  if (rc) return fail(h, -2, "tensor map encode failed (rc=%d)", rc);
-  const int64_t stats_bytes = align_up(static_cast<int64_t>(M) * 6 * 8, 1024);
-  const int groups = (M + 255) / 256 * 8;
-  if (workspace_bytes < 2 * stats_bytes + 2 * groups * 4) return fail(h, -1, "test_gemm_ln: workspace too small");
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  uint8_t* ws = static_cast<uint8_t*>(workspace);
-  LnFuse f{};
-  f.mode = mode & 15;
-  f.dbg = mode >> 4;      // probes (tools/ln_probe.py); results are then undefined
-  f.g = g; f.b = b; f.g2 = g2; f.b2 = b2;
-  f.out16 = static_cast<__half*>(out16);
-  f.rope16 = static_cast<__half*>(rope16);
-  f.xout = xout;
-  f.stats = reinterpret_cast<float2*>(ws);
-  f.stats2 = reinterpret_cast<float2*>(ws + stats_bytes);
-  f.cnt = reinterpret_cast<unsigned int*>(ws + 2 * stats_bytes);
-  f.cnt2 = f.cnt + groups;
-  f.rope_cos = h->w.rope_cos;
-  f.rope_sin = h->w.rope_sin;
-  f.T = T;
-  f.half_dim = c.d_model / c.n_heads / 2;
-  f.eps = 1e-5f;
-  cudaMemsetAsync(f.cnt, 0, 2 * groups * 4, s);
-  {
-    PROF(PC_MISC);
-    rc = launch_gemm_res_ln(&ta, &tw, M, K, bias, x, x, scale, f, h->num_sms, s);
-  }
-  if (rc) return fail(h, -4, "gemm_res_ln launch rejected (rc=%d): %s", rc, cudaGetErrorString(cudaGetLastError()));
-  GAM_CHECK_LAUNCH(h, "test_gemm_ln");
   return 0;
 }
 

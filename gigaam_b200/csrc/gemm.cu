@@ -20,12 +20,12 @@ int launch_v2(const CUtensorMap* ta, const CUtensorMap* tw, GemmParams p, int nu
   const int max_pairs = num_sms / 2;
   const int npairs = tiles < max_pairs ? tiles : max_pairs;
   if (npairs <= 0) return 0;
-  return launch_k(kern, dim3(2 * npairs), dim3(G2Cfg<EPI>::kThreads), G2Cfg<EPI>::kSmem, s, *ta, ta2 ? *ta2 : *ta, *tw, p) == cudaSuccess ? 0 : -2;
+  return launch_k(kern, dim3(2 * npairs), dim3(kG2Threads), kG2Smem, s, *ta, ta2 ? *ta2 : *ta, *tw, p) == cudaSuccess ? 0 : -2;
 }
 
 template <int EPI, int AMODE>
 int set_attr() {
-  return cudaFuncSetAttribute(gemm2_f16_tn_kernel<EPI, AMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2Cfg<EPI>::kSmem) == cudaSuccess ? 0 : -1;
+  return cudaFuncSetAttribute(gemm2_f16_tn_kernel<EPI, AMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kG2Smem) == cudaSuccess ? 0 : -1;
 }
 
 }  // namespace
@@ -37,7 +37,6 @@ int gemm_init() {
   rc |= set_attr<EPI_BIAS_GLU_F16, A_2D>();
   rc |= set_attr<EPI_BIAS_RES_F32, A_2D>();
   rc |= set_attr<EPI_BIAS_F32, A_2D>();
-  rc |= set_attr<EPI_BIAS_RES_LN_F32, A_2D>();
   rc |= set_attr<EPI_CONV_RELU_MASK_F16, A_CONV>();
   rc |= set_attr<EPI_POWER_F32, A_2D>();
   rc |= set_attr<EPI_CONV_RELU_MASK_F16, A_CONV1D>();
@@ -67,27 +66,6 @@ int launch_gemm(int kind, const CUtensorMap* ta, const CUtensorMap* tw, int M, i
     case GEMM_BIAS_F32: return launch_v2<EPI_BIAS_F32, A_2D>(ta, tw, p, num_sms, s);
     default: return -1;
   }
-}
-
-// x = res + scale * (A W^T + bias) (fp32, N = 768) followed by the LayerNorm(s) described by `ln` (gemm_params.cuh: LnFuse)
-// in the same launch.  The cross-CTA statistics exchange needs the three n-tiles of a 256-row block to run on different,
-// co-resident CTA pairs: at least 3 pairs, grid <= #SMs (always true here).
-int launch_gemm_res_ln(const CUtensorMap* ta, const CUtensorMap* tw, int M, int K, const float* bias, const float* res, float* out,
-                       float scale, const LnFuse& ln, int num_sms, cudaStream_t s) {
-  if (K % kGemmBK != 0 || M <= 0 || num_sms < 6 || ln.mode < 1 || ln.mode > 3) return -1;
-  GemmParams p{};
-  p.M = M;
-  p.N = kLnD;
-  p.num_m_tiles = (M + kGemmBM - 1) / kGemmBM;
-  p.num_n_tiles = kLnD / kBN;
-  p.num_k_blocks = K / kGemmBK;
-  p.bias = bias;
-  p.res = res;
-  p.out = out;
-  p.ldo = kLnD;
-  p.scale = scale;
-  p.ln = ln;
-  return launch_v2<EPI_BIAS_RES_LN_F32, A_2D>(ta, tw, p, num_sms, s);
 }
 
 // D[:, :n1] = A1 W[:n1]^T + b, D[:, n1:] = A2 W[n1:]^T + b  (fp16 out) in ONE launch of the pair kernel: more tiles per

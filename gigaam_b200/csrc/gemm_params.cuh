@@ -22,34 +22,6 @@ enum GemmEpilogue : int {
   EPI_CONV_RELU_MASK_F16 = 5,  // out16 = t2 < len2[b] ? relu(acc + bias) : 0   (A_CONV / A_CONV1D row mapping)
   EPI_CONV_RELU_MASK_F32 = 6,  // out32 = t < len[b] ? relu(acc + bias) : 0      (A_CONV1D, last subsampling stage)
   EPI_POWER_F32 = 7,           // out32[:, n] = re^2 + im^2, tile = [128 re | 128 im]  (DFT power spectrum, no bias)
-  EPI_BIAS_RES_LN_F32 = 8,     // EPI_BIAS_RES_F32 + the LayerNorm(s) that follow it in the layer, see LnFuse
-};
-
-// LayerNorm fused behind the residual epilogue of an N = 768 GEMM (gigaam/encoder.py:481-497: every residual add of a
-// Conformer layer is followed by a LayerNorm of the full 768-wide row, whose fp16 result is the next GEMM's A operand).
-// A 256 x 256 tile sees a third of a row, so the row statistics are exchanged through global memory: every epilogue warp
-// writes (sum, sum of squares) of its 32 rows x 128 columns into its own slot (fixed slots, fixed summation order:
-// deterministic), bumps a per-32-row counter with release semantics, waits until the six slots of its rows have
-// arrived, and normalises the values it has just written (re-read from L2).  Needs all CTAs of the grid co-resident
-// (persistent grid <= #SMs, 1 CTA / SM: true for every launch of this kernel).
-//   mode 1: out16 = LN(x)                                  norm_conv, norm_feed_forward2 (and norm_self_att for rel_pos)
-//   mode 2: out16 = u = LN(x), rope16 = rope(u)            norm_self_att of the rotary models (utils.py:83-100)
-//   mode 3: xout = LN(x) fp32; out16 = LN2(xout) if g2     norm_out (+ the next layer's norm_feed_forward1)
-struct LnFuse {
-  int mode;                    // 0 = off
-  const float *g, *b;          // first LayerNorm affine [768]
-  const float *g2, *b2;        // mode 3: second LayerNorm affine, or null (last layer)
-  __half* out16;               // [M, 768]
-  __half* rope16;              // mode 2
-  float* xout;                 // mode 3 (may alias the GEMM output)
-  float2* stats;               // [M_pad, 6] partial (sum, sumsq): slot = 2 * n_tile + column half
-  float2* stats2;              // mode 3, second round
-  unsigned int* cnt;           // [M_pad / 32] arrivals per 32-row group, zero on entry
-  unsigned int* cnt2;          // mode 3, second round
-  const float *rope_cos, *rope_sin;   // [max_len, half_dim]
-  int T, half_dim;
-  float eps;
-  int dbg;                     // timing probes of tools/ln_probe.py only: 1 = skip the wait, 2 = stop after the exchange
 };
 
 // A_CONV  : implicit im2col of a 3x3 / stride-2 conv2d over channels-last [B, T1, F1, C]  (4-D strided TMA)
@@ -78,7 +50,6 @@ struct GemmParams {
   // pair kernel, A_2D only: n-tiles [0, a1_nblks) read A through tmap_a, the rest through tmap_a2 (0 = tmap_a for all).
   // Lets two GEMMs that share M, K and the output buffer but not the A operand (W_qk on rope(u), W_v on u) run as one launch.
   int a1_nblks;
-  LnFuse ln;   // EPI_BIAS_RES_LN_F32
 };
 
 constexpr int kGemmBM = 128;

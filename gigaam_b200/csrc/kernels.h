@@ -57,7 +57,6 @@ int launch_rnnt_greedy_cluster(const float* encproj, const int* len, const float
 
 // gemm.cu
 struct GemmParams;
-struct LnFuse;
 enum GemmKind : int {
   GEMM_BIAS_F16 = 0,
   GEMM_BIAS_SILU_F16 = 1,
@@ -69,9 +68,6 @@ enum GemmKind : int {
 // 2-D operand GEMM  D[M,N] = A[M,K] W[N,K]^T with fused epilogue `kind`; N % 256 == 0, K % 64 == 0.
 int launch_gemm(int kind, const CUtensorMap* tmap_a, const CUtensorMap* tmap_w, int M, int N, int K, const float* bias,
                 const float* res, void* out, int ldo, float scale, int num_sms, cudaStream_t s);
-// x = res + scale * (A W^T + bias) with the following LayerNorm(s) fused behind it (gemm_params.cuh: LnFuse); N = 768
-int launch_gemm_res_ln(const CUtensorMap* tmap_a, const CUtensorMap* tmap_w, int M, int K, const float* bias, const float* res,
-                       float* out, float scale, const LnFuse& ln, int num_sms, cudaStream_t s);
 // one launch for two GEMMs that share M, K, W's row space and the output buffer but read different A operands:
 // columns [0, n1) from tmap_a1, [n1, N) from tmap_a2 (bias -> fp16).  
 int launch_gemm_dual_a(const CUtensorMap* tmap_a1, const CUtensorMap* tmap_a2, int n1, const CUtensorMap* tmap_w, int M, int N,

@@ -193,14 +193,6 @@ int gam_group_words(gam_handle* h, const int32_t* ids, const int32_t* frames, co
  * 3 res + scale*(acc+bias) -> f32, 4 bias -> f32).  A, W fp16 device; N % 256 == 0; K % 64 == 0. */
 int gam_test_gemm(gam_handle* h, int32_t kind, const void* A, const void* W, const float* bias, const float* res, void* out,
                   int32_t M, int32_t N, int32_t K, int32_t ldo, float scale, void* stream);
-/* The residual GEMM of a Conformer layer with the LayerNorm(s) that follow it fused behind the epilogue
- * (gigaam/encoder.py:481-497): x[M,768] += scale * (A[M,K] W[768,K]^T + bias) in place, then
- *   mode 1: out16 = LN(x; g, b)                      mode 2: out16 = u = LN(x; g, b), rope16 = rotary(u) with t = row % T
- *   mode 3: xout = LN(x; g, b) fp32 (may alias x); out16 = LN(xout; g2, b2) unless g2 == NULL
- * workspace: >= 2 * align1024(M * 48) + 2 * ceil(M / 256) * 32 bytes. */
-int gam_test_gemm_ln(gam_handle* h, int32_t mode, const void* A, const void* W, const float* bias, float* x, const float* g,
-                     const float* b, const float* g2, const float* b2, void* out16, void* rope16, float* xout, int32_t M, int32_t K,
-                     int32_t T, float scale, void* workspace, int64_t workspace_bytes, void* stream);
 /* qkv: f16 [B*T, 3*d_model]; klen i32 [B] or NULL -> out f16 [B*T, d_model] */
 int gam_test_attention(gam_handle* h, const void* qkv, const int32_t* klen, void* out, int32_t B, int32_t T, void* stream);
 /* rel_pos variant: qkv f16 [B*T, 4*d_model] = [q+u | q+v | k | v]; pos f16 [2*GAM_REL_POS_MAX_T-1, d_model] */

