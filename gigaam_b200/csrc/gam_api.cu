@@ -115,6 +115,7 @@ struct gam_handle {
   int device = 0;
   int num_sms = 148;
   int64_t launches = 0;
+  bool zigzag = true;        // alternate the row direction of consecutive kernels (GemmParams::reverse)
   void* comm = nullptr;      // ncclComm_t of gam_comm_init
   int comm_rank = 0, comm_nranks = 1;
   std::string err;
@@ -298,6 +299,7 @@ int gam_create(const gam_config* cfg, const gam_weights* w, int device, gam_hand
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(h, -11, "cudaGetDeviceProperties failed");
   if (prop.major != 10) return fail(h, -12, "sm_100a kernels need a Blackwell (cc 10.x) device, found cc %d.%d", prop.major, prop.minor);
   h->num_sms = prop.multiProcessorCount;
+  { const char* e = getenv("GAM_ZIGZAG_OFF"); h->zigzag = !(e && e[0] == '1'); }   // TEMPORARY A/B switch (removed once measured)
   if (init_encode() != 0) return fail(h, -13, "cuTensorMapEncodeTiled entry point not available");
   if (gemm_init() != 0) return fail(h, -14, "cudaFuncSetAttribute failed for the GEMM kernels: %s", cudaGetErrorString(cudaGetLastError()));
   h->layers.assign(w->layers, w->layers + c.n_layers);
@@ -489,9 +491,14 @@ int gam_encode(gam_handle* h, const float* mel, const int64_t* mel_len, int32_t 
     GAM_CHECK_LAUNCH(h, "subsampling");
     if (rc) return fail(h, -4, "conv1d subsampling launch rejected (rc=%d)", rc);
   }
+  // Direction plan of a layer (GemmParams::reverse): every kernel walks the rows in the direction OPPOSITE to the one its
+  // main input was written in, so that it starts on what is still in L2.  U = ascending, D = descending:
+  //   LN_ff1 D | FF1-up U | FF1-down D | LN_att U | QKV D | attention U | proj D | LN_conv U | pw1 D | depthwise U | pw2 D |
+  //   LN_ff2 U | FF2-up D | FF2-down U | LN_out (+ next LN_ff1) D
+  const int zz = h->zigzag ? 1 : 0;
   if (L > 0) {
     PROF(PC_LAYERNORM);
-    launch_ln_f16(p->x, h->layers[0].ln_ff1_g, h->layers[0].ln_ff1_b, p->a16, R, s);
+    launch_ln_f16(p->x, h->layers[0].ln_ff1_g, h->layers[0].ln_ff1_b, p->a16, R, zz, s);
   }
   const int dk = d / c.n_heads;
   for (int l = 0; l < L; ++l) {
@@ -499,62 +506,62 @@ int gam_encode(gam_handle* h, const float* mel, const int64_t* mel_len, int32_t 
     const LayerMaps& m = h->lmaps[l];
     // x += 0.5 * FF1(LN(x))                                     (encoder.py:480-483)
     { PROF(PC_GEMM_FFN_UP);
-      rc |= launch_gemm(GEMM_BIAS_SILU_F16, &p->m_a16, &m.ff1_w1, R, c.d_ff, d, w.ff1_b1, nullptr, p->big16, c.d_ff, 1.f, nsm, s); }
+      rc |= launch_gemm(GEMM_BIAS_SILU_F16, &p->m_a16, &m.ff1_w1, R, c.d_ff, d, w.ff1_b1, nullptr, p->big16, c.d_ff, 1.f, nsm, s, 0); }
     { PROF(PC_GEMM_FFN_DOWN);
-      rc |= launch_gemm(GEMM_BIAS_RES_F32, &p->m_hid, &m.ff1_w2, R, d, c.d_ff, w.ff1_b2, p->x, p->x, d, 0.5f, nsm, s); }
+      rc |= launch_gemm(GEMM_BIAS_RES_F32, &p->m_hid, &m.ff1_w2, R, d, c.d_ff, w.ff1_b2, p->x, p->x, d, 0.5f, nsm, s, zz); }
     // x += W_o attn(q = W_q rope(u), k = W_k rope(u), v = W_v u), u = LN(x)   (encoder.py:485-487, 236-277)
     if (c.self_attention == 0) {
       { PROF(PC_LAYERNORM);
-        launch_ln_rope_f16(p->x, w.ln_att_g, w.ln_att_b, h->w.rope_cos, h->w.rope_sin, p->a16, p->r16, R, p->T2, dk / 2, s); }
+        launch_ln_rope_f16(p->x, w.ln_att_g, w.ln_att_b, h->w.rope_cos, h->w.rope_sin, p->a16, p->r16, R, p->T2, dk / 2, 0, s); }
       bool merged = false;
       if (m.qkv_merged) {
         PROF(PC_GEMM_QKV);
-        merged = launch_gemm_dual_a(&p->m_r16, &p->m_a16, 2 * d, &m.w_qkv, R, 3 * d, d, w.b_qk, p->big16, 3 * d, nsm, s) == 0;
+        merged = launch_gemm_dual_a(&p->m_r16, &p->m_a16, 2 * d, &m.w_qkv, R, 3 * d, d, w.b_qk, p->big16, 3 * d, nsm, s, zz) == 0;
       }
       if (!merged) {
         { PROF(PC_GEMM_QKV);
-          rc |= launch_gemm(GEMM_BIAS_F16, &p->m_r16, &m.w_qk, R, 2 * d, d, w.b_qk, nullptr, p->big16, 3 * d, 1.f, nsm, s); }
+          rc |= launch_gemm(GEMM_BIAS_F16, &p->m_r16, &m.w_qk, R, 2 * d, d, w.b_qk, nullptr, p->big16, 3 * d, 1.f, nsm, s, zz); }
         { PROF(PC_GEMM_QKV);
-          rc |= launch_gemm(GEMM_BIAS_F16, &p->m_a16, &m.w_v, R, d, d, w.b_v, nullptr, p->big16 + 2 * d, 3 * d, 1.f, nsm, s); }
+          rc |= launch_gemm(GEMM_BIAS_F16, &p->m_a16, &m.w_v, R, d, d, w.b_v, nullptr, p->big16 + 2 * d, 3 * d, 1.f, nsm, s, zz); }
       }
       { PROF(PC_ATTENTION);
         rc |= launch_attention(&p->m_qkv, B > 1 ? p->len2 : nullptr, p->o16, B, p->T2, c.n_heads, dk, d, nsm, s); }
     } else {
       // rel_pos (encoder.py:208-228): one projection GEMM -> [q+u | q+v | k | v], position scores inside the kernel
       { PROF(PC_LAYERNORM);
-        launch_ln_f16(p->x, w.ln_att_g, w.ln_att_b, p->a16, R, s); }
+        launch_ln_f16(p->x, w.ln_att_g, w.ln_att_b, p->a16, R, 0, s); }
       { PROF(PC_GEMM_QKV);
-        rc |= launch_gemm(GEMM_BIAS_F16, &p->m_a16, &m.w_qkv_rel, R, 4 * d, d, w.b_qkv_rel, nullptr, p->big16, 4 * d, 1.f, nsm, s); }
+        rc |= launch_gemm(GEMM_BIAS_F16, &p->m_a16, &m.w_qkv_rel, R, 4 * d, d, w.b_qkv_rel, nullptr, p->big16, 4 * d, 1.f, nsm, s, zz); }
       { PROF(PC_ATTENTION);
         rc |= launch_attention_relpos(&p->m_qkv4, &m.pos_proj, B > 1 ? p->len2 : nullptr, p->o16, B, p->T2, c.n_heads, dk, d, s); }
     }
     { PROF(PC_GEMM_PROJ);
-      rc |= launch_gemm(GEMM_BIAS_RES_F32, &p->m_o16, &m.w_o, R, d, d, w.b_o, p->x, p->x, d, 1.f, nsm, s); }
+      rc |= launch_gemm(GEMM_BIAS_RES_F32, &p->m_o16, &m.w_o, R, d, d, w.b_o, p->x, p->x, d, 1.f, nsm, s, zz); }
     // x += Conv(LN(x))                                           (encoder.py:489-491, 396-409)
     { PROF(PC_LAYERNORM);
-      launch_ln_f16(p->x, w.ln_conv_g, w.ln_conv_b, p->a16, R, s); }
+      launch_ln_f16(p->x, w.ln_conv_g, w.ln_conv_b, p->a16, R, 0, s); }
     { PROF(PC_GEMM_GLU);
-      rc |= launch_gemm(GEMM_BIAS_GLU_F16, &p->m_a16, &m.pw1, R, 2 * d, d, w.pw1_b, nullptr, p->g16, d, 1.f, nsm, s); }
+      rc |= launch_gemm(GEMM_BIAS_GLU_F16, &p->m_a16, &m.pw1, R, 2 * d, d, w.pw1_b, nullptr, p->g16, d, 1.f, nsm, s, zz); }
     { PROF(PC_DWCONV);
       if (c.conv_norm == 0)
         rc |= launch_dwconv_bn_silu(p->g16, w.dw_w, w.dw_b, p->len2, p->o16, B, p->T2, c.conv_kernel_size, s);
       else
         rc |= launch_dwconv_ln_silu(p->g16, w.dw_w, w.dw_b, w.cn_g, w.cn_b, p->len2, p->o16, B, p->T2, c.conv_kernel_size, s); }
     { PROF(PC_GEMM_PROJ);
-      rc |= launch_gemm(GEMM_BIAS_RES_F32, &p->m_o16, &m.pw2, R, d, d, w.pw2_b, p->x, p->x, d, 1.f, nsm, s); }
+      rc |= launch_gemm(GEMM_BIAS_RES_F32, &p->m_o16, &m.pw2, R, d, d, w.pw2_b, p->x, p->x, d, 1.f, nsm, s, zz); }
     // x += 0.5 * FF2(LN(x))                                      (encoder.py:493-495)
     { PROF(PC_LAYERNORM);
-      launch_ln_f16(p->x, w.ln_ff2_g, w.ln_ff2_b, p->a16, R, s); }
+      launch_ln_f16(p->x, w.ln_ff2_g, w.ln_ff2_b, p->a16, R, 0, s); }
     { PROF(PC_GEMM_FFN_UP);
-      rc |= launch_gemm(GEMM_BIAS_SILU_F16, &p->m_a16, &m.ff2_w1, R, c.d_ff, d, w.ff2_b1, nullptr, p->big16, c.d_ff, 1.f, nsm, s); }
+      rc |= launch_gemm(GEMM_BIAS_SILU_F16, &p->m_a16, &m.ff2_w1, R, c.d_ff, d, w.ff2_b1, nullptr, p->big16, c.d_ff, 1.f, nsm, s, zz); }
     { PROF(PC_GEMM_FFN_DOWN);
-      rc |= launch_gemm(GEMM_BIAS_RES_F32, &p->m_hid, &m.ff2_w2, R, d, c.d_ff, w.ff2_b2, p->x, p->x, d, 0.5f, nsm, s); }
+      rc |= launch_gemm(GEMM_BIAS_RES_F32, &p->m_hid, &m.ff2_w2, R, d, c.d_ff, w.ff2_b2, p->x, p->x, d, 0.5f, nsm, s, 0); }
     // x = LN_out(x) (+ next layer's first LN fused)                (encoder.py:497)
     { PROF(PC_LAYERNORM);
       if (l + 1 < L)
-        launch_ln_out_ln(p->x, w.ln_out_g, w.ln_out_b, h->layers[l + 1].ln_ff1_g, h->layers[l + 1].ln_ff1_b, p->x, p->a16, R, s);
+        launch_ln_out_ln(p->x, w.ln_out_g, w.ln_out_b, h->layers[l + 1].ln_ff1_g, h->layers[l + 1].ln_ff1_b, p->x, p->a16, R, zz, s);
       else
-        launch_ln_out_ln(p->x, w.ln_out_g, w.ln_out_b, nullptr, nullptr, enc, nullptr, R, s); }
+        launch_ln_out_ln(p->x, w.ln_out_g, w.ln_out_b, nullptr, nullptr, enc, nullptr, R, zz, s); }
     if (rc) return fail(h, -4, "layer %d: a launch was rejected (rc=%d): %s", l, rc, cudaGetErrorString(cudaGetLastError()));
   }
   cudaMemcpyAsync(enc_len, p->len2, B * sizeof(int), cudaMemcpyDeviceToDevice, s);

@@ -45,7 +45,7 @@ int gemm_init() {
 }
 
 int launch_gemm(int kind, const CUtensorMap* ta, const CUtensorMap* tw, int M, int N, int K, const float* bias,
-                const float* res, void* out, int ldo, float scale, int num_sms, cudaStream_t s) {
+                const float* res, void* out, int ldo, float scale, int num_sms, cudaStream_t s, int reverse) {
   if (N % kBN != 0 || K % kGemmBK != 0 || M <= 0) return -1;
   GemmParams p{};
   p.M = M;
@@ -58,6 +58,7 @@ int launch_gemm(int kind, const CUtensorMap* ta, const CUtensorMap* tw, int M, i
   p.out = out;
   p.ldo = ldo;
   p.scale = scale;
+  p.reverse = reverse;
   switch (kind) {
     case GEMM_BIAS_F16: return launch_v2<EPI_BIAS_F16, A_2D>(ta, tw, p, num_sms, s);
     case GEMM_BIAS_SILU_F16: return launch_v2<EPI_BIAS_SILU_F16, A_2D>(ta, tw, p, num_sms, s);
@@ -71,7 +72,7 @@ int launch_gemm(int kind, const CUtensorMap* ta, const CUtensorMap* tw, int M, i
 // D[:, :n1] = A1 W[:n1]^T + b, D[:, n1:] = A2 W[n1:]^T + b  (fp16 out) in ONE launch of the pair kernel: more tiles per
 // launch = less wave quantisation (QK + V: 378 + 189 tiles on 74 pairs = 6 + 3 waves apart, 8 together) and one launch less.
 int launch_gemm_dual_a(const CUtensorMap* ta1, const CUtensorMap* ta2, int n1, const CUtensorMap* tw, int M, int N, int K,
-                       const float* bias, void* out, int ldo, int num_sms, cudaStream_t s) {
+                       const float* bias, void* out, int ldo, int num_sms, cudaStream_t s, int reverse) {
   if (N % kBN != 0 || n1 % kBN != 0 || n1 <= 0 || n1 >= N || K % kGemmBK != 0 || M <= 0) return -1;
   GemmParams p{};
   p.M = M;
@@ -84,6 +85,7 @@ int launch_gemm_dual_a(const CUtensorMap* ta1, const CUtensorMap* ta2, int n1, c
   p.ldo = ldo;
   p.scale = 1.f;
   p.a1_nblks = n1 / kBN;
+  p.reverse = reverse;
   return launch_v2<EPI_BIAS_F16, A_2D>(ta1, tw, p, num_sms, s, ta2);
 }
 

@@ -88,8 +88,9 @@ gemm2_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = pair; tile < num_tiles; tile += npairs) {
-        const int m_pair = tile / p.num_n_tiles;
-        const int n_blk = tile % p.num_n_tiles;
+        const int tl = p.reverse ? num_tiles - 1 - tile : tile;
+        const int m_pair = tl / p.num_n_tiles;
+        const int n_blk = tl % p.num_n_tiles;
         const int m_blk = m_pair * 2 + static_cast<int>(rank);   // this CTA's 128-row block
         const CUtensorMap* ta = (p.a1_nblks > 0 && n_blk >= p.a1_nblks) ? &tmap_a2 : &tmap_a;
         int conv_b = 0, conv_t0 = 0;
@@ -169,8 +170,9 @@ gemm2_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = pair; tile < num_tiles; tile += npairs) {
-      const int m_pair = tile / p.num_n_tiles;
-      const int n_blk = tile % p.num_n_tiles;
+      const int tl = p.reverse ? num_tiles - 1 - tile : tile;
+      const int m_pair = tl / p.num_n_tiles;
+      const int n_blk = tl % p.num_n_tiles;
       const int m_blk = m_pair * 2 + static_cast<int>(rank);
       // this warp's 128 bias values -> smem for broadcast reads
       if constexpr (EPI != EPI_POWER_F32) {
@@ -229,8 +231,8 @@ gemm2_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         // residual stream is fp32 and mostly DRAM-resident, and 8 epilogue warps cannot cover DRAM latency with the two
         // chunks (16 loads per thread) they keep in flight -- the N = 768 GEMMs are bound by exactly these loads
         if constexpr (AMODE == A_2D) {
-          const int nt = tile + npairs;
-          if (nt < num_tiles) {
+          if (tile + npairs < num_tiles) {
+            const int nt = p.reverse ? num_tiles - 1 - (tile + npairs) : tile + npairs;
             const long long row = (static_cast<long long>(nt / p.num_n_tiles) * 2 + static_cast<long long>(rank)) * 128 + quad * 32 + lane;
             if (row < p.M) {
               const float* src = p.res + static_cast<size_t>(row) * p.ldo + static_cast<size_t>(nt % p.num_n_tiles) * BN + half * 128;

@@ -50,6 +50,11 @@ struct GemmParams {
   // pair kernel, A_2D only: n-tiles [0, a1_nblks) read A through tmap_a, the rest through tmap_a2 (0 = tmap_a for all).
   // Lets two GEMMs that share M, K and the output buffer but not the A operand (W_qk on rope(u), W_v on u) run as one launch.
   int a1_nblks;
+  // A_2D only: walk the tiles from the last row block to the first.  Consecutive kernels of a layer alternate direction
+  // (gam_api.cu): a consumer then starts on the rows its producer wrote LAST, which are the ones still in the 126 MB L2 --
+  // read in the producer's own order, a buffer that does not fit is evicted just ahead of the reader (LRU) and every
+  // byte comes from DRAM.
+  int reverse;
 };
 
 constexpr int kGemmBM = 128;

@@ -8,11 +8,12 @@
 namespace gam {
 
 // rowops.cu
-void launch_ln_f16(const float* x, const float* g, const float* b, __half* out, int rows, cudaStream_t s);
+// `reverse`: walk the rows from the last to the first (see GemmParams::reverse: consecutive kernels alternate direction)
+void launch_ln_f16(const float* x, const float* g, const float* b, __half* out, int rows, int reverse, cudaStream_t s);
 void launch_ln_rope_f16(const float* x, const float* g, const float* b, const float* rope_cos, const float* rope_sin,
-                        __half* out_u, __half* out_r, int rows, int T, int half_dim, cudaStream_t s);
+                        __half* out_u, __half* out_r, int rows, int T, int half_dim, int reverse, cudaStream_t s);
 void launch_ln_out_ln(const float* r, const float* g_out, const float* b_out, const float* g_next, const float* b_next,
-                      float* x_out, __half* y_out, int rows, cudaStream_t s);
+                      float* x_out, __half* y_out, int rows, int reverse, cudaStream_t s);
 int launch_dwconv_bn_silu(const __half* g, const float* w, const float* bias, const int* len, __half* out, int B, int T,
                           int kw, cudaStream_t s);
 int launch_dwconv_ln_silu(const __half* g, const float* w, const float* bias, const float* gamma, const float* beta,
@@ -67,11 +68,11 @@ enum GemmKind : int {
 };
 // 2-D operand GEMM  D[M,N] = A[M,K] W[N,K]^T with fused epilogue `kind`; N % 256 == 0, K % 64 == 0.
 int launch_gemm(int kind, const CUtensorMap* tmap_a, const CUtensorMap* tmap_w, int M, int N, int K, const float* bias,
-                const float* res, void* out, int ldo, float scale, int num_sms, cudaStream_t s);
+                const float* res, void* out, int ldo, float scale, int num_sms, cudaStream_t s, int reverse = 0);
 // one launch for two GEMMs that share M, K, W's row space and the output buffer but read different A operands:
 // columns [0, n1) from tmap_a1, [n1, N) from tmap_a2 (bias -> fp16).  
 int launch_gemm_dual_a(const CUtensorMap* tmap_a1, const CUtensorMap* tmap_a2, int n1, const CUtensorMap* tmap_w, int M, int N,
-                       int K, const float* bias, void* out, int ldo, int num_sms, cudaStream_t s);
+                       int K, const float* bias, void* out, int ldo, int num_sms, cudaStream_t s, int reverse = 0);
 // implicit-GEMM 3x3/s2 conv over channels-last [B,T1,F1,C] (tmap_a 4-D strided), output [B*T2*16, N] fp16
 int launch_gemm_conv(const CUtensorMap* tmap_a4d, const CUtensorMap* tmap_w, int B, int T2, int C, int N, const float* bias,
                      const int* len2, void* out, int ldo, int num_sms, cudaStream_t s);

@@ -43,6 +43,15 @@ __device__ __forceinline__ void load_row_stats(const float* __restrict__ row, in
   rstd = rsqrtf(warp_sum(q) * (1.0f / kD) + eps);
 }
 
+// Row handled by warp `w` of block `blk`; `reverse` = the LAST rows first.  The residual GEMM that has just written x
+// streamed ~120 MB through the 126 MB L2, so the rows it wrote first are evicted and the rows it wrote last are still
+// resident: a LayerNorm that walks the rows in the OPPOSITE direction turns an LRU-pathological re-read (0 % hits) into
+// hits on everything still cached (gam_api.cu alternates the direction kernel by kernel).
+__device__ __forceinline__ int ln_row(int blk, int w, int rows, int reverse) {
+  const int r = blk * 8 + w;
+  return r >= rows ? -1 : (reverse ? rows - 1 - r : r);
+}
+
 __device__ __forceinline__ float4 ln_apply(float4 v, float mean, float rstd, float4 g, float4 b) {
   return make_float4((v.x - mean) * rstd * g.x + b.x, (v.y - mean) * rstd * g.y + b.y,
                      (v.z - mean) * rstd * g.z + b.z, (v.w - mean) * rstd * g.w + b.w);
@@ -56,10 +65,10 @@ __device__ __forceinline__ uint2 pack4(float4 v) {
 // ------------------------------------------------------------------ LN -> fp16
 __global__ void __launch_bounds__(256) ln_f16_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                      const float* __restrict__ beta, __half* __restrict__ out,
-                                                     int rows, float eps) {
+                                                     int rows, int reverse, float eps) {
   const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (row >= rows) return;
+  const int row = ln_row(blockIdx.x, threadIdx.x >> 5, rows, reverse);
+  if (row < 0) return;
   float4 v[kVec];
   float mean, rstd;
   load_row_stats(x + static_cast<size_t>(row) * kD, lane, v, mean, rstd, eps);
@@ -79,12 +88,12 @@ __global__ void __launch_bounds__(256) ln_rope_f16_kernel(const float* __restric
                                                           const float* __restrict__ rope_cos,
                                                           const float* __restrict__ rope_sin, __half* __restrict__ out_u,
                                                           __half* __restrict__ out_r, int rows, int T, int half_dim,
-                                                          float eps) {
+                                                          int reverse, float eps) {
   __shared__ float srow[8][kD];
   const int lane = threadIdx.x & 31;
   const int w = threadIdx.x >> 5;
-  const int row = blockIdx.x * 8 + w;
-  if (row >= rows) return;
+  const int row = ln_row(blockIdx.x, w, rows, reverse);
+  if (row < 0) return;
   float4 v[kVec];
   float mean, rstd;
   load_row_stats(x + static_cast<size_t>(row) * kD, lane, v, mean, rstd, eps);
@@ -125,10 +134,10 @@ __global__ void __launch_bounds__(256) ln_rope_f16_kernel(const float* __restric
 __global__ void __launch_bounds__(256) ln_out_ln_kernel(const float* __restrict__ r, const float* __restrict__ g_out,
                                                         const float* __restrict__ b_out, const float* __restrict__ g_next,
                                                         const float* __restrict__ b_next, float* __restrict__ x_out,
-                                                        __half* __restrict__ y_out, int rows, float eps) {
+                                                        __half* __restrict__ y_out, int rows, int reverse, float eps) {
   const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (row >= rows) return;
+  const int row = ln_row(blockIdx.x, threadIdx.x >> 5, rows, reverse);
+  if (row < 0) return;
   float4 v[kVec];
   float mean, rstd;
   load_row_stats(r + static_cast<size_t>(row) * kD, lane, v, mean, rstd, eps);
@@ -288,16 +297,16 @@ __global__ void sub_lengths_kernel(const long long* __restrict__ mel_len, int B,
 }  // namespace
 
 // ------------------------------------------------------------------ launchers
-void launch_ln_f16(const float* x, const float* g, const float* b, __half* out, int rows, cudaStream_t s) {
-  launch_k(ln_f16_kernel, dim3((rows + 7) / 8), dim3(256), 0, s, x, g, b, out, rows, 1e-5f);
+void launch_ln_f16(const float* x, const float* g, const float* b, __half* out, int rows, int reverse, cudaStream_t s) {
+  launch_k(ln_f16_kernel, dim3((rows + 7) / 8), dim3(256), 0, s, x, g, b, out, rows, reverse, 1e-5f);
 }
 void launch_ln_rope_f16(const float* x, const float* g, const float* b, const float* rc, const float* rs, __half* out_u,
-                        __half* out_r, int rows, int T, int half_dim, cudaStream_t s) {
-  launch_k(ln_rope_f16_kernel, dim3((rows + 7) / 8), dim3(256), 0, s, x, g, b, rc, rs, out_u, out_r, rows, T, half_dim, 1e-5f);
+                        __half* out_r, int rows, int T, int half_dim, int reverse, cudaStream_t s) {
+  launch_k(ln_rope_f16_kernel, dim3((rows + 7) / 8), dim3(256), 0, s, x, g, b, rc, rs, out_u, out_r, rows, T, half_dim, reverse, 1e-5f);
 }
 void launch_ln_out_ln(const float* r, const float* g_out, const float* b_out, const float* g_next, const float* b_next,
-                      float* x_out, __half* y_out, int rows, cudaStream_t s) {
-  launch_k(ln_out_ln_kernel, dim3((rows + 7) / 8), dim3(256), 0, s, r, g_out, b_out, g_next, b_next, x_out, y_out, rows, 1e-5f);
+                      float* x_out, __half* y_out, int rows, int reverse, cudaStream_t s) {
+  launch_k(ln_out_ln_kernel, dim3((rows + 7) / 8), dim3(256), 0, s, r, g_out, b_out, g_next, b_next, x_out, y_out, rows, reverse, 1e-5f);
 }
 int launch_dwconv_bn_silu(const __half* g, const float* w, const float* bias, const int* len, __half* out, int B, int T,
                           int kw, cudaStream_t s) {
