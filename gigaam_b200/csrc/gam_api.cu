@@ -115,7 +115,6 @@ struct gam_handle {
   int device = 0;
   int num_sms = 148;
   int64_t launches = 0;
-  bool zigzag = true;        // alternate the row direction of consecutive kernels (GemmParams::reverse)
   void* comm = nullptr;      // ncclComm_t of gam_comm_init
   int comm_rank = 0, comm_nranks = 1;
   std::string err;
@@ -299,7 +298,6 @@ int gam_create(const gam_config* cfg, const gam_weights* w, int device, gam_hand
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(h, -11, "cudaGetDeviceProperties failed");
   if (prop.major != 10) return fail(h, -12, "sm_100a kernels need a Blackwell (cc 10.x) device, found cc %d.%d", prop.major, prop.minor);
   h->num_sms = prop.multiProcessorCount;
-  { const char* e = getenv("GAM_ZIGZAG_OFF"); h->zigzag = !(e && e[0] == '1'); }   // TEMPORARY A/B switch (removed once measured)
   if (init_encode() != 0) return fail(h, -13, "cuTensorMapEncodeTiled entry point not available");
   if (gemm_init() != 0) return fail(h, -14, "cudaFuncSetAttribute failed for the GEMM kernels: %s", cudaGetErrorString(cudaGetLastError()));
   h->layers.assign(w->layers, w->layers + c.n_layers);
@@ -495,7 +493,8 @@ int gam_encode(gam_handle* h, const float* mel, const int64_t* mel_len, int32_t 
   // main input was written in, so that it starts on what is still in L2.  U = ascending, D = descending:
   //   LN_ff1 D | FF1-up U | FF1-down D | LN_att U | QKV D | attention U | proj D | LN_conv U | pw1 D | depthwise U | pw2 D |
   //   LN_ff2 U | FF2-up D | FF2-down U | LN_out (+ next LN_ff1) D
-  const int zz = h->zigzag ? 1 : 0;
+  // Measured on c2 (same box, alternating runs, profiles/r2f_zigzag_ab.md): 12.47 ms per step one-directional, 12.27 ms alternating.
+  constexpr int zz = 1;
   if (L > 0) {
     PROF(PC_LAYERNORM);
     launch_ln_f16(p->x, h->layers[0].ln_ff1_g, h->layers[0].ln_ff1_b, p->a16, R, zz, s);
