@@ -193,8 +193,8 @@ def c4_strong_scaling(dev, rank: int, world: int, steps: int = 3, total: int = 2
     eng = model._get_engine()
     s0, s1 = shard_bounds(total, rank, world)
     rows = (total + world - 1) // world
-    wav, wav_len = gigaam.synthetic_audio(s1 - s0, seconds, seed=1234 + rank)
-    wav, wav_len = wav.to(dev), wav_len.to(dev)
+    wav, wav_len = gigaam.synthetic_audio(total, seconds, seed=1234)     # the SAME 256 utterances whatever N is ...
+    wav, wav_len = wav[s0:s1].to(dev), wav_len[s0:s1].to(dev)            # ... this rank's contiguous shard of them
     T = eng.encoded_frames(eng.logmel_frames(wav.shape[1]))
     W = eng.hyp_width(T)
     gather = HypothesisGather(eng) if world > 1 else None
