@@ -24,7 +24,8 @@ assert len(_CHAR_VOCAB) == 33
 
 # Per-model calibration of the synthetic RNN-T joint network, written by oracle/calibrate_rnnt.py (random weights
 # otherwise emit max_symbols tokens on every frame or none at all): the mean encoder frame that
-# `head.joint.enc.bias` cancels and the blank-logit bias that lands the token rate on BASELINE.md's target.
+# `head.joint.enc.bias` cancels, the utterance-to-utterance directions `head.joint.enc.weight` is made blind to, and the
+# blank-logit bias that lands the token rate on BASELINE.md's target.
 RNNT_CALIBRATION_FILE = Path(__file__).with_name("rnnt_calibration.npz")
 
 
@@ -239,6 +240,10 @@ def synthetic_state_dict(cfg: Dict, seed: int = 0, rnnt_calibration: Optional[Di
     head = cfg.get("head")
     if head and head["type"] == "rnnt":
         cal = _rnnt_calibration(cfg["model_name"]) if rnnt_calibration is None else rnnt_calibration
+        if "enc_null" in cal:       # rows orthogonal to the directions in which utterance means differ (oracle/calibrate_rnnt.py)
+            null = torch.as_tensor(cal["enc_null"])
+            w = sd["head.joint.enc.weight"]
+            sd["head.joint.enc.weight"] = w - (w @ null.t()) @ null
         if "enc_mean" in cal:
             sd["head.joint.enc.bias"] = -(sd["head.joint.enc.weight"] @ torch.as_tensor(cal["enc_mean"]))
         sd["head.joint.joint_net.1.bias"][-1] += float(cal.get("blank_bias", 0.0))
