@@ -432,7 +432,12 @@ def main():
         if tr.exists():
             traffic = json.loads(tr.read_text()).get(name)
         roofline = {"kernel": name, "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                    "frac": (achieved / peak_tf) if achieved else None, "traffic": traffic, "peak_source": peak_src,
+                    "frac": (achieved / peak_tf) if achieved else None, "traffic": traffic,
+                    "traffic_source": "profiles/ncu_traffic.json: dram bytes per launch from the committed ncu --set full capture "
+                                      "(cold L2), not measured in this run",
+                    "classes_note": "per-launch CUDA events around eager launches: the classes sum to more than ms_per_step (one "
+                                    "CUDA graph, no launch gaps); use them for shares",
+                    "peak_source": peak_src,
                     "avg_launch_ms": avg_ms, "launches_per_step": n // nprof, "share_of_step": ms_sum / total_ms,
                     "flops_per_launch": fpl,
                     "step_tflops": B * fl["total"] / (ms_per_step * 1e-3) / 1e12,
