@@ -52,7 +52,7 @@ EXPORTS = ("gam_create", "gam_destroy", "gam_last_error", "gam_version", "gam_lo
            "gam_test_attention", "gam_launch_count", "gam_profile_begin", "gam_profile_end", "gam_profile_class_count",
            "gam_profile_class_name", "gam_logmel_workspace_bytes", "gam_logmel_tc", "gam_test_attention_relpos",
            "gam_decode_workspace_bytes", "gam_group_words", "gam_comm_unique_id", "gam_comm_init",
-           "gam_comm_nccl_version", "gam_gather_hyps")
+           "gam_comm_nccl_version", "gam_gather_hyps", "gam_test_attention_varlen")
 
 
 def lib_path() -> Path:
@@ -110,6 +110,8 @@ def load() -> C.CDLL:
     lib.gam_test_attention.restype = C.c_int
     lib.gam_test_attention_relpos.argtypes = [H, c_vp, c_vp, c_vp, c_vp, i32, i32, c_vp]
     lib.gam_test_attention_relpos.restype = C.c_int
+    lib.gam_test_attention_varlen.argtypes = [H, c_vp, c_vp, c_vp, c_vp, c_vp, i32, i32, i32, c_vp]
+    lib.gam_test_attention_varlen.restype = C.c_int
     lib.gam_logmel_workspace_bytes.argtypes = [H, i32, i64]
     lib.gam_logmel_workspace_bytes.restype = i64
     lib.gam_logmel_tc.argtypes = [H, c_vp, i32, i64, c_vp, c_vp, i64, c_vp]

@@ -2,9 +2,10 @@
 // Replaces RelPositionMultiHeadAttention.forward (gigaam/encoder.py:208-228) + forward_attention (:173-188) on
 // the output of ONE projection GEMM whose weight is [W_q ; W_q ; W_k ; W_v] and whose bias carries pos_bias_u / _v:
 //
-//   qkv : [B*T, 4*768] fp16 = [q+u | q+v | k | v], head h at columns h*48 .. h*48+47 of each part
+//   qkv : [rows, 4*768] fp16 = [q+u | q+v | k | v], head h at columns h*48 .. h*48+47 of each part; rows are packed
+//         (utterance b = rows cu[b] .. cu[b] + klen[b]; cu == null: the padded [B, T] layout of the unit tests)
 //   pos : [2*kRelPosMaxT-1, 768] fp16 = W_pos pe(r) for r = kRelPosMaxT-1 ... -(kRelPosMaxT-1)   (row = kRelPosMaxT-1-r)
-//   out : [B*T, 768] fp16
+//   out : [rows, 768] fp16
 //
 //   s[i, j] = ((q_i+u) . k_j + (q_i+v) . p_{i-j}) / sqrt(d_k)          p_r = pos row for relative position r
 //
@@ -38,6 +39,7 @@ constexpr uint32_t kOCol = 128, kBDCol = 256;
 struct RelParams {
   int T;
   const int* klen;   // may be null
+  const int* cu;     // may be null (padded rows)
   __half* out;
   int ld_out;        // d_model
   int dk;
@@ -86,10 +88,13 @@ __global__ void __launch_bounds__(kThreads, 1) attention_relpos_kernel(const __g
   const int q0 = blockIdx.x * 128;
   const int h = blockIdx.y;
   const int b = blockIdx.z;
-  const int row0 = b * p.T;
-  const int dmodel = p.ld_out;
   int klen = p.T;
   if (p.klen != nullptr) klen = min(max(p.klen[b], 0), p.T);
+  // packed rows: a query tile past the utterance's last frame has nothing to compute or store (uniform for the CTA)
+  if (p.cu != nullptr && q0 >= klen) return;
+  const int row0 = p.cu != nullptr ? __ldg(p.cu + b) : b * p.T;
+  const int qlim = p.cu != nullptr ? klen : p.T;   // query rows that are stored
+  const int dmodel = p.ld_out;
   const int nkb = (klen + 127) >> 7;   // key blocks that hold at least one valid key
 
   if (warp_idx == 0 && ptx::elect_one()) {
@@ -193,6 +198,13 @@ __global__ void __launch_bounds__(kThreads, 1) attention_relpos_kernel(const __g
       ptx::mbar_wait(s_full, kb & 1);
       ptx::tc_fence_after();
       const int nvalid = min(klen - kb * 128, 128);
+      // S of this block exists => its K / V / position tiles have landed: clear the V rows past klen (their P is 0, but
+      // 0 x stale inf / NaN bits would not be); made visible to the tensor core by the proxy fence before p_full below
+      if (nvalid < 128 && r >= nvalid) {
+        uint4* vrow = reinterpret_cast<uint4*>(sStage + (kb & 1) * kStageBytes + kTile + r * 128);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) vrow[j] = make_uint4(0u, 0u, 0u, 0u);
+      }
       // ---- sweep A: s = ac + shifted bd, written back over the ac columns; block maximum
       float bm = -INFINITY;
 #pragma unroll 1
@@ -288,7 +300,7 @@ __global__ void __launch_bounds__(kThreads, 1) attention_relpos_kernel(const __g
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = 0u;
       }
-      if (q < p.T) {
+      if (q < qlim) {
         uint32_t o[8];
 #pragma unroll
         for (int j = 0; j < 16; j += 2) {
@@ -314,10 +326,10 @@ constexpr int kSmemBytes = 4 * kTile + 2 * kStageBytes + kSkewBytes + 128 + 1024
 
 }  // namespace
 
-int launch_attention_relpos(const CUtensorMap* tmap_qkv, const CUtensorMap* tmap_pos, const int* klen, __half* out, int B, int T,
-                            int H, int dk, int d_model, cudaStream_t s) {
+int launch_attention_relpos(const CUtensorMap* tmap_qkv, const CUtensorMap* tmap_pos, const int* klen, const int* cu, __half* out,
+                            int B, int T, int H, int dk, int d_model, cudaStream_t s) {
   const int nkb = (T + 127) / 128;
-  if (nkb > kMaxKB || T > kRelPosMaxT || dk % 16 != 0 || dk > 64) return -1;
+  if (nkb > kMaxKB || T > kRelPosMaxT || dk % 16 != 0 || dk > 64 || (cu != nullptr && klen == nullptr)) return -1;
   static PerDeviceOnce attr_once;
   if (attr_once.first() &&
       cudaFuncSetAttribute(attention_relpos_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess)
@@ -325,6 +337,7 @@ int launch_attention_relpos(const CUtensorMap* tmap_qkv, const CUtensorMap* tmap
   RelParams p;
   p.T = T;
   p.klen = klen;
+  p.cu = cu;
   p.out = out;
   p.ld_out = d_model;
   p.dk = dk;

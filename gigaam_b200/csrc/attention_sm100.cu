@@ -3,8 +3,14 @@
 // gigaam/encoder.py:258-277 (RotaryPositionMultiHeadAttention) on the q/k/v produced by the fused
 // LN+RoPE -> GEMM kernels.
 //
-//   qkv : [B*T, 2304] fp16 = [q(768) | k(768) | v(768)], head h at columns h*48 .. h*48+47 of each part
-//   out : [B*T, 768]  fp16
+//   qkv : [rows, 2304] fp16 = [q(768) | k(768) | v(768)], head h at columns h*48 .. h*48+47 of each part
+//   out : [rows, 768]  fp16
+//
+// Rows are PACKED (the varlen contract of gigaam/utils.py:103-155, apply_masked_flash_attn): utterance b owns rows
+// cu[b] .. cu[b] + klen[b]; only the query tiles and key blocks that hold one of its frames are computed, a tile that
+// reaches past the utterance reads its neighbour's rows (masked as keys, never stored as queries).  With cu == null the
+// layout is the padded [B, T] one (unit tests): row b*T, every query row stored.  The rows of the last key block past
+// klen are zeroed in shared memory before P.V: their P is 0, but 0 x (stale inf / NaN bits) would not be.
 //
 // Common to both kernels below: K / V blocks are 128 keys x 64 columns (SWIZZLE_128B; the 16 columns past the 48
 // real ones belong to the next head and are never multiplied: QK^T runs K = 3 x 16 and the 16 extra output columns
@@ -28,6 +34,42 @@ __device__ __forceinline__ float ex2(float x) {
 }
 
 
+// geometry of one (utterance, head) item; identical in every warp role
+struct ItemGeom {
+  int row0;   // first row of the utterance
+  int klen;   // valid keys
+  int qlim;   // query rows that are stored
+  int nq;     // query tiles that are computed (0: the item is skipped by every role)
+  int nk;     // key blocks that are multiplied (>= 1)
+};
+__device__ __forceinline__ ItemGeom item_geom(const int* klen_p, const int* cu, int b, int T, int nkb) {
+  ItemGeom g;
+  g.klen = klen_p != nullptr ? min(max(__ldg(klen_p + b), 0), T) : T;
+  const int kb = (g.klen + 127) >> 7;
+  g.nk = max(1, kb);
+  if (cu != nullptr) {
+    g.row0 = __ldg(cu + b);
+    g.qlim = g.klen;
+    g.nq = kb;
+  } else {
+    g.row0 = b * T;
+    g.qlim = T;
+    g.nq = nkb;
+  }
+  return g;
+}
+
+// rows of key block kb_last past klen -> 0 in the V tile (SWIZZLE_128B permutes 16-byte chunks inside a 128-byte row, so
+// clearing whole rows needs no address arithmetic); thread = row.  Followed by the generic -> async proxy fence.
+__device__ __forceinline__ void zero_v_tail(uint8_t* v_tile, int r, int valid_rows) {
+  if (r >= valid_rows) {
+    uint4* row = reinterpret_cast<uint4*>(v_tile + r * 128);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) row[j] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  ptx::fence_proxy_async_smem();
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Persistent variant for T <= 256 (the headline config, T' = 251): one CTA per SM loops over (utterance, head)
 // work items.  Q/K/V of item i+1 stream into the other half of a double-buffered smem ring while item i is in
@@ -37,6 +79,7 @@ __device__ __forceinline__ float ex2(float x) {
 struct AttnPersParams {
   int T, nkb, B, H;
   const int* klen;
+  const int* cu;
   __half* out;
   int ld_out, dk;
   float scale_log2;
@@ -82,12 +125,15 @@ __global__ void __launch_bounds__(128 + 256, 1) attention_persistent_kernel(cons
   if (warp_idx == 0) {
     // ===================================================== TMA producer
     if (ptx::elect_one()) {
-      int it = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      int it = 0;   // items that use the ring (an utterance without frames is skipped by every role)
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int b = item / p.H, h = item % p.H;
+        const ItemGeom g = item_geom(p.klen, p.cu, b, p.T, nkb);
+        if (g.nq == 0) continue;
         const int buf = it & 1;
         const uint32_t par = (it >> 1) & 1;
-        const int b = item / p.H, h = item % p.H;
-        const int row0 = b * p.T;
+        ++it;
+        const int row0 = g.row0;
         uint8_t* sQ = smem + buf * item_bytes;
         uint8_t* sK = sQ + nkb * kTileBytes;
         uint8_t* sV = sK + nkb * kTileBytes;
@@ -108,19 +154,32 @@ __global__ void __launch_bounds__(128 + 256, 1) attention_persistent_kernel(cons
       constexpr uint32_t kIdescS = ptx::make_idesc_f16(128, 128, 0, 0);
       constexpr uint32_t kIdescPV = ptx::make_idesc_f16(128, 64, 0, 1);   // B (= V) MN-major; A (= P) from TMEM
       const int ksteps_qk = p.dk / 16;
-      int it = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      int it = 0;        // ring position (shared by both streams)
+      uint32_t n_mine = 0;   // items this stream has computed: parity of its own s / p / o barriers
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const ItemGeom g = item_geom(p.klen, p.cu, item / p.H, p.T, nkb);
+        if (g.nq == 0) continue;
         const int buf = it & 1;
-        const uint32_t ipar = it & 1;
+        const uint32_t kv_par = (it >> 1) & 1;
+        ++it;
         uint8_t* sQ = smem + buf * item_bytes;
         uint8_t* sK = sQ + nkb * kTileBytes;
         uint8_t* sV = sK + nkb * kTileBytes;
-        ptx::mbar_wait(&kv_full[buf], (it >> 1) & 1);
+        ptx::mbar_wait(&kv_full[buf], kv_par);
+        if (qt >= g.nq) {
+          // this stream's query tile holds no frame of the utterance: only release the ring slot (after the wait above, so
+          // that a stream can never arrive twice within one phase of kv_empty)
+          if (ptx::elect_one()) ptx::mbar_arrive(&kv_empty[buf]);
+          __syncwarp();
+          continue;
+        }
+        const uint32_t ipar = n_mine & 1;
+        ++n_mine;
         ptx::mbar_wait(&o_empty[qt], ipar ^ 1);   // previous item's O has been read out of this tile's region
         ptx::tc_fence_after();
         if (ptx::elect_one()) {
           const uint32_t qa = ptx::smem_u32(sQ + qt * kTileBytes);
-          for (int kb = 0; kb < nkb; ++kb) {
+          for (int kb = 0; kb < g.nk; ++kb) {
             const uint32_t ka = ptx::smem_u32(sK + kb * kTileBytes);
             for (int k = 0; k < ksteps_qk; ++k)
               ptx::mma_f16_ss(tmem_base + qt * 256 + kb * 128, ptx::make_smem_desc_sw128(qa + k * 32, 16, 1024),
@@ -132,7 +191,7 @@ __global__ void __launch_bounds__(128 + 256, 1) attention_persistent_kernel(cons
         ptx::mbar_wait(&p_full[qt], ipar);
         ptx::tc_fence_after();
         if (ptx::elect_one()) {
-          for (int kb = 0; kb < nkb; ++kb) {
+          for (int kb = 0; kb < g.nk; ++kb) {
             const uint32_t va = ptx::smem_u32(sV + kb * kTileBytes);
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks)
@@ -153,14 +212,22 @@ __global__ void __launch_bounds__(128 + 256, 1) attention_persistent_kernel(cons
     const int r = quad * 32 + lane;
     const uint32_t t_s = tmem_base + qt * 256 + (static_cast<uint32_t>(quad * 32) << 16);
     int it = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-      const uint32_t ipar = it & 1;
+    uint32_t n_mine = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int b = item / p.H, h = item % p.H;
-      int klen = p.T;
-      if (p.klen != nullptr) klen = min(max(p.klen[b], 0), p.T);
+      const ItemGeom g = item_geom(p.klen, p.cu, b, p.T, nkb);
+      if (g.nq == 0) continue;
+      const int buf = it & 1;
+      ++it;
+      if (qt >= g.nq) continue;
+      const uint32_t ipar = n_mine & 1;
+      ++n_mine;
+      const int klen = g.klen;
       const int nchunks = (klen + 31) >> 5;
-      ptx::mbar_wait(&s_full[qt], ipar);
+      ptx::mbar_wait(&s_full[qt], ipar);   // S complete => this item's Q / K / V have all landed (one kv_full transaction)
       ptx::tc_fence_after();
+      if (klen < g.nk * 128)
+        zero_v_tail(smem + buf * item_bytes + (2 * nkb + g.nk - 1) * kTileBytes, r, klen - (g.nk - 1) * 128);
       // Both sweeps are software-pipelined over two register buffers: the TMEM load of chunk c+1 is in flight while
       // chunk c is reduced / exponentiated (tcgen05.wait::ld waits for every outstanding load, so the next load is
       // issued right after the wait and before the math).
@@ -245,7 +312,7 @@ __global__ void __launch_bounds__(128 + 256, 1) attention_persistent_kernel(cons
         uint32_t zero[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) zero[j] = 0u;
-        for (int c = nchunks; c < nkb * 4; ++c) ptx::tmem_st_32x32b_x16(t_s + c * 16, zero);
+        for (int c = nchunks; c < g.nk * 4; ++c) ptx::tmem_st_32x32b_x16(t_s + c * 16, zero);
       }
       ptx::tmem_st_wait();
       ptx::tc_fence_before();
@@ -264,8 +331,8 @@ __global__ void __launch_bounds__(128 + 256, 1) attention_persistent_kernel(cons
       sum += sum1;
       const float inv = sum > 0.f ? 1.0f / sum : 0.f;
       const int q = qt * 128 + r;
-      if (q < p.T) {
-        __half* dst = p.out + (static_cast<size_t>(b) * p.T + q) * p.ld_out + h * p.dk;
+      if (q < g.qlim) {
+        __half* dst = p.out + (static_cast<size_t>(g.row0) + q) * p.ld_out + h * p.dk;
 #pragma unroll
         for (int c = 0; c < 48; c += 8) {
           if (c < p.dk) {
@@ -299,6 +366,7 @@ __global__ void __launch_bounds__(128 + 256, 1) attention_persistent_kernel(cons
 struct AttnLongParams {
   int T, nkb, H;
   const int* klen;
+  const int* cu;
   __half* out;
   int ld_out, dk;
   float scale_log2;
@@ -310,7 +378,9 @@ __global__ void __launch_bounds__(kLongThreads, 1) attention_long_kernel(const _
                                                                        const AttnLongParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int nkb = p.nkb;
+  const ItemGeom g = item_geom(p.klen, p.cu, blockIdx.x / p.H, p.T, p.nkb);
+  if (g.nq == 0) return;                       // packed rows: the utterance has no frame (uniform for the CTA)
+  const int nkb = g.nk;                        // key blocks with a valid key (>= 1); shared memory is sized for p.nkb
   uint8_t* sK = smem;                          // [nkb]
   uint8_t* sV = sK + nkb * kTileBytes;         // [nkb]
   uint8_t* sQ = sV + nkb * kTileBytes;         // [2] one per warpgroup
@@ -326,10 +396,10 @@ __global__ void __launch_bounds__(kLongThreads, 1) attention_long_kernel(const _
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_full + 14);
 
   const int warp_idx = threadIdx.x >> 5;
-  const int h = blockIdx.x % p.H, b = blockIdx.x / p.H;
-  const int row0 = b * p.T;
+  const int h = blockIdx.x % p.H;
+  const int row0 = g.row0;
   const int dmodel = p.ld_out;
-  const int nqt = nkb;
+  const int nqt = g.nq;
 
   if (warp_idx == 0 && ptx::elect_one()) {
     ptx::prefetch_tmap(&tmap_qkv);
@@ -420,8 +490,7 @@ __global__ void __launch_bounds__(kLongThreads, 1) attention_long_kernel(const _
     const int lane = threadIdx.x & 31;
     const int r = quad * 32 + lane;
     const uint32_t t_s = tmem_base + wg * 256 + (static_cast<uint32_t>(quad * 32) << 16);
-    int klen = p.T;
-    if (p.klen != nullptr) klen = min(max(p.klen[b], 0), p.T);
+    const int klen = g.klen;
     uint32_t n_s = 0;
     int it = 0;
     for (int qt = wg; qt < nqt; qt += 2, ++it) {
@@ -429,6 +498,9 @@ __global__ void __launch_bounds__(kLongThreads, 1) attention_long_kernel(const _
       for (int kb = 0; kb < nkb; ++kb, ++n_s) {
         ptx::mbar_wait(&s_full[wg], n_s & 1);
         ptx::tc_fence_after();
+        // S of block kb exists => kv_full[kb] completed => V[kb] has landed: clear its rows past klen once per warpgroup,
+        // long before this warpgroup's first P.V over the block (ordered by its later p_full arrivals)
+        if (it == 0 && kb == nkb - 1 && klen < nkb * 128) zero_v_tail(sV + kb * kTileBytes, r, klen - kb * 128);
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
           const int key0 = kb * 128 + c * 32;
@@ -489,7 +561,7 @@ __global__ void __launch_bounds__(kLongThreads, 1) attention_long_kernel(const _
       if (lane == 0) ptx::mbar_arrive(&o_empty[wg]);
       const float inv = sum > 0.f ? 1.0f / sum : 0.f;
       const int q = qt * 128 + r;
-      if (q < p.T) {
+      if (q < g.qlim) {
         __half* dst = p.out + (static_cast<size_t>(row0) + q) * p.ld_out + h * p.dk;
 #pragma unroll
         for (int c = 0; c < 48; c += 8) {
@@ -517,13 +589,14 @@ __global__ void __launch_bounds__(kLongThreads, 1) attention_long_kernel(const _
 
 }  // namespace
 
-static int launch_attention_long(const CUtensorMap* tmap_qkv, const int* klen, __half* out, int B, int T, int H, int dk,
-                                 int d_model, cudaStream_t s) {
+static int launch_attention_long(const CUtensorMap* tmap_qkv, const int* klen, const int* cu, __half* out, int B, int T, int H,
+                                 int dk, int d_model, cudaStream_t s) {
   AttnLongParams p;
   p.T = T;
   p.nkb = (T + 127) / 128;
   p.H = H;
   p.klen = klen;
+  p.cu = cu;
   p.out = out;
   p.ld_out = d_model;
   p.dk = dk;
@@ -537,14 +610,15 @@ static int launch_attention_long(const CUtensorMap* tmap_qkv, const int* klen, _
   return 0;
 }
 
-static int launch_attention_persistent(const CUtensorMap* tmap_qkv, const int* klen, __half* out, int B, int T, int H, int dk,
-                                       int d_model, int num_sms, cudaStream_t s) {
+static int launch_attention_persistent(const CUtensorMap* tmap_qkv, const int* klen, const int* cu, __half* out, int B, int T,
+                                       int H, int dk, int d_model, int num_sms, cudaStream_t s) {
   AttnPersParams p;
   p.T = T;
   p.nkb = (T + 127) / 128;
   p.B = B;
   p.H = H;
   p.klen = klen;
+  p.cu = cu;
   p.out = out;
   p.ld_out = d_model;
   p.dk = dk;
@@ -558,12 +632,12 @@ static int launch_attention_persistent(const CUtensorMap* tmap_qkv, const int* k
   const int smem = 2 * 3 * p.nkb * kTileBytes + 256 + 1024;
   return launch_k(attention_persistent_kernel, dim3(grid), dim3(128 + 128 * p.nkb), smem, s, *tmap_qkv, p) == cudaSuccess ? 0 : -2;
 }
-int launch_attention(const CUtensorMap* tmap_qkv, const int* klen, __half* out, int B, int T, int H, int dk, int d_model,
-                     int num_sms, cudaStream_t s) {
+int launch_attention(const CUtensorMap* tmap_qkv, const int* klen, const int* cu, __half* out, int B, int T, int H, int dk,
+                     int d_model, int num_sms, cudaStream_t s) {
   const int nkb = (T + 127) / 128;
-  if (nkb > kMaxKB || dk % 16 != 0 || dk > 64) return -1;
-  if (nkb <= 2) return launch_attention_persistent(tmap_qkv, klen, out, B, T, H, dk, d_model, num_sms, s);
-  return launch_attention_long(tmap_qkv, klen, out, B, T, H, dk, d_model, s);
+  if (nkb > kMaxKB || dk % 16 != 0 || dk > 64 || (cu != nullptr && klen == nullptr)) return -1;
+  if (nkb <= 2) return launch_attention_persistent(tmap_qkv, klen, cu, out, B, T, H, dk, d_model, num_sms, s);
+  return launch_attention_long(tmap_qkv, klen, cu, out, B, T, H, dk, d_model, s);
 }
 
 }  // namespace gam

@@ -150,12 +150,13 @@ __global__ void __launch_bounds__(256) logmel_kernel(const float* __restrict__ w
 // mel is [B, F, M] (feature-major as produced by the front end); the conv runs on its transpose
 // [B,1,M,F] (gigaam/encoder.py:609-611).  block = (t1, b); 256 threads; thread = 3 channels x all f1.
 __global__ void __launch_bounds__(256) subsample_conv1_kernel(const float* __restrict__ mel, const int* __restrict__ len0,
-                                                              const int* __restrict__ len1, const float* __restrict__ w,
-                                                              const float* __restrict__ bias, __half* __restrict__ out,
-                                                              int M, int F, int T1, int F1, int C) {
+                                                              const int* __restrict__ len1, const int* __restrict__ run1,
+                                                              const float* __restrict__ w, const float* __restrict__ bias,
+                                                              __half* __restrict__ out, int M, int F, int T1, int F1, int C) {
   constexpr int kTT = 8;                      // output time steps per block (weights stay in registers across them)
   __shared__ float patch[2 * kTT + 1][72];    // mel rows 2 t1_0 - 1 .. 2 t1_0 + 2 kTT - 1, features -1..F  (F <= 70)
   const int t1_0 = blockIdx.x * kTT, b = blockIdx.y;
+  if (run1 != nullptr && t1_0 >= __ldg(run1 + b)) return;   // no kept stage-2 frame reads these rows (pack_plan_kernel)
   const int L0 = len0[b], L1 = len1[b];
   for (int i = threadIdx.x; i < (2 * kTT + 1) * (F + 2); i += blockDim.x) {
     const int rr = i / (F + 2), ff = i % (F + 2) - 1;
@@ -344,11 +345,11 @@ int launch_logmel(const float* wav, int B, int n_samples, int n_frames, const fl
   return 0;
 }
 
-int launch_subsample_conv1(const float* mel, const int* len0, const int* len1, const float* w, const float* bias,
+int launch_subsample_conv1(const float* mel, const int* len0, const int* len1, const int* run1, const float* w, const float* bias,
                            __half* out, int B, int M, int F, int T1, int F1, int C, cudaStream_t s) {
   if (F > 70 || C % 8 != 0 || C / 8 > 128) return -1;
   dim3 grid((T1 + 7) / 8, B);
-  subsample_conv1_kernel<<<grid, 2 * (C / 8), 0, s>>>(mel, len0, len1, w, bias, out, M, F, T1, F1, C);
+  subsample_conv1_kernel<<<grid, 2 * (C / 8), 0, s>>>(mel, len0, len1, run1, w, bias, out, M, F, T1, F1, C);
   return 0;
 }
 

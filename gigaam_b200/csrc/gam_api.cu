@@ -91,6 +91,9 @@ struct Plan {
   int T1 = 0, F1 = 0, T2 = 0, F2 = 0, R = 0;
   // workspace carve-up
   int *len0 = nullptr, *len1 = nullptr, *len2 = nullptr;
+  // packed-row plan (pack_plan_kernel): frames kept per utterance, their prefix sum [B + 1], the live row count, the
+  // stage-1 frames that are produced, and row -> (utterance, frame)
+  int *plen = nullptr, *cu = nullptr, *rows_dev = nullptr, *run1 = nullptr, *row_b = nullptr, *row_t = nullptr;
   __half *s1 = nullptr, *s2 = nullptr, *a16 = nullptr, *r16 = nullptr, *big16 = nullptr, *o16 = nullptr, *g16 = nullptr;
   __half* melT = nullptr;   // conv1d subsampling: time-major fp16 copy of the log-mel
   CUtensorMap m_melT, m_s1_3d;
@@ -198,6 +201,12 @@ int64_t plan_carve(const gam_handle* h, Plan* p, uint8_t* base) {
   p->len0 = reinterpret_cast<int*>(take(B * 4));
   p->len1 = reinterpret_cast<int*>(take(B * 4));
   p->len2 = reinterpret_cast<int*>(take(B * 4));
+  p->plen = reinterpret_cast<int*>(take(B * 4));
+  p->run1 = reinterpret_cast<int*>(take(B * 4));
+  p->cu = reinterpret_cast<int*>(take((B + 1) * 4));
+  p->rows_dev = reinterpret_cast<int*>(take(4));
+  p->row_b = reinterpret_cast<int*>(take(R * 4));
+  p->row_t = reinterpret_cast<int*>(take(R * 4));
   p->x = reinterpret_cast<float*>(take(R * d * 4));
   p->a16 = reinterpret_cast<__half*>(take(R * d * 2));
   p->r16 = reinterpret_cast<__half*>(take(R * d * 2));
@@ -448,27 +457,32 @@ int gam_encode(gam_handle* h, const float* mel, const int64_t* mel_len, int32_t 
   const int L = (n_layers_run < 0 || n_layers_run > c.n_layers) ? c.n_layers : n_layers_run;
   int rc = 0;
 
+  // Varlen execution: from the second subsampling stage on, the path keeps only the frames that exist.  Utterance b owns rows
+  // cu[b] .. cu[b] + plen[b] of every activation matrix (plen = its subsampled length; a batch of one keeps all T' frames,
+  // like the reference's mask-free single-utterance attention); the live row count stays on the device (rows_dev), so the
+  // same launch sequence -- and a captured CUDA graph of it -- serves every mix of lengths.  Grids are sized for R = B*T'.
   {
     PROF(PC_MISC);
-    launch_sub_lengths(reinterpret_cast<const long long*>(mel_len), B, 2 * ((c.subs_kernel_size - 1) / 2) - c.subs_kernel_size,
-                       static_cast<int>(M), p->len0, p->len1, p->len2, s);
+    launch_pack_plan(reinterpret_cast<const long long*>(mel_len), B, 2 * ((c.subs_kernel_size - 1) / 2) - c.subs_kernel_size,
+                     static_cast<int>(M), p->T1, p->T2, p->len0, p->len1, p->len2, p->plen, p->run1, p->cu, p->rows_dev, p->row_b,
+                     p->row_t, s);
   }
-  float* xdst = (L == 0) ? enc : p->x;  // n_layers_run == 0 -> return pre_encode output
+  const int* rdev = p->rows_dev;
   if (c.subsampling == 0) {
     {
       PROF(PC_SUB_CONV1);
-      rc |= launch_subsample_conv1(mel, p->len0, p->len1, h->w.sub1_w, h->w.sub1_b, p->s1, B, static_cast<int>(M), c.feat_in,
+      rc |= launch_subsample_conv1(mel, p->len0, p->len1, p->run1, h->w.sub1_w, h->w.sub1_b, p->s1, B, static_cast<int>(M), c.feat_in,
                                    p->T1, p->F1, d, s);
     }
     {
       PROF(PC_GEMM_CONV2);
-      rc |= launch_gemm_conv(&p->m_s1, &h->m_sub2_w, B, p->T2, d, d, h->w.sub2_b, p->len2, p->s2, d, nsm, s);
+      rc |= launch_gemm_conv(&p->m_s1, &h->m_sub2_w, B, p->T2, d, d, h->w.sub2_b, p->len2, p->cu, p->plen, p->s2, d, nsm, s);
     }
     GAM_CHECK_LAUNCH(h, "subsampling");
     if (rc) return fail(h, -4, "subsampling launch rejected (rc=%d)", rc);
     {
       PROF(PC_GEMM_SUBOUT);
-      rc |= launch_gemm(GEMM_BIAS_F32, &p->m_s2, &h->m_sub_out_w, R, d, p->F2 * d, h->w.sub_out_b, nullptr, xdst, d, 1.f, nsm, s);
+      rc |= launch_gemm(GEMM_BIAS_F32, &p->m_s2, &h->m_sub_out_w, R, d, p->F2 * d, h->w.sub_out_b, nullptr, p->x, d, 1.f, nsm, s, 0, rdev);
     }
   } else {
     // conv1d subsampling (gigaam/encoder.py:59-70 with Conv1d): two k-tap / stride-2 implicit GEMMs over time-major data
@@ -478,13 +492,13 @@ int gam_encode(gam_handle* h, const float* mel, const int64_t* mel_len, int32_t 
     }
     {
       PROF(PC_GEMM_CONV2);
-      rc |= launch_gemm_conv1d(&p->m_melT, &h->m_sub2_w, B, p->T1, c.feat_in, c.subs_kernel_size, d, h->w.c1d_b1, p->len1, p->s1, d,
-                               0, nsm, s);
+      rc |= launch_gemm_conv1d(&p->m_melT, &h->m_sub2_w, B, p->T1, c.feat_in, c.subs_kernel_size, d, h->w.c1d_b1, p->len1, nullptr,
+                               nullptr, p->s1, d, 0, nsm, s);   // stage 1 stays [B, T1]: stage 2 fetches it with 3-D TMA boxes
     }
     {
       PROF(PC_GEMM_SUBOUT);
-      rc |= launch_gemm_conv1d(&p->m_s1_3d, &h->m_sub_out_w, B, p->T2, d, c.subs_kernel_size, d, h->w.c1d_b2, p->len2, xdst, d, 1,
-                               nsm, s);
+      rc |= launch_gemm_conv1d(&p->m_s1_3d, &h->m_sub_out_w, B, p->T2, d, c.subs_kernel_size, d, h->w.c1d_b2, p->len2, p->cu,
+                               p->plen, p->x, d, 1, nsm, s);
     }
     GAM_CHECK_LAUNCH(h, "subsampling");
     if (rc) return fail(h, -4, "conv1d subsampling launch rejected (rc=%d)", rc);
@@ -495,9 +509,12 @@ int gam_encode(gam_handle* h, const float* mel, const int64_t* mel_len, int32_t 
   //   LN_ff2 U | FF2-up D | FF2-down U | LN_out (+ next LN_ff1) D
   // Measured on c2 (same box, alternating runs, profiles/r2f_zigzag_ab.md): 12.47 ms per step one-directional, 12.27 ms alternating.
   constexpr int zz = 1;
-  if (L > 0) {
+  if (L == 0) {   // n_layers_run == 0: the caller wants the pre_encode output
+    PROF(PC_MISC);
+    launch_unpack_rows(p->x, nullptr, nullptr, p->cu, p->plen, enc, B, p->T2, 0, s);
+  } else {
     PROF(PC_LAYERNORM);
-    launch_ln_f16(p->x, h->layers[0].ln_ff1_g, h->layers[0].ln_ff1_b, p->a16, R, zz, s);
+    launch_ln_f16(p->x, h->layers[0].ln_ff1_g, h->layers[0].ln_ff1_b, p->a16, R, rdev, zz, s);
   }
   const int dk = d / c.n_heads;
   for (int l = 0; l < L; ++l) {
@@ -505,62 +522,64 @@ int gam_encode(gam_handle* h, const float* mel, const int64_t* mel_len, int32_t 
     const LayerMaps& m = h->lmaps[l];
     // x += 0.5 * FF1(LN(x))                                     (encoder.py:480-483)
     { PROF(PC_GEMM_FFN_UP);
-      rc |= launch_gemm(GEMM_BIAS_SILU_F16, &p->m_a16, &m.ff1_w1, R, c.d_ff, d, w.ff1_b1, nullptr, p->big16, c.d_ff, 1.f, nsm, s, 0); }
+      rc |= launch_gemm(GEMM_BIAS_SILU_F16, &p->m_a16, &m.ff1_w1, R, c.d_ff, d, w.ff1_b1, nullptr, p->big16, c.d_ff, 1.f, nsm, s, 0, rdev); }
     { PROF(PC_GEMM_FFN_DOWN);
-      rc |= launch_gemm(GEMM_BIAS_RES_F32, &p->m_hid, &m.ff1_w2, R, d, c.d_ff, w.ff1_b2, p->x, p->x, d, 0.5f, nsm, s, zz); }
+      rc |= launch_gemm(GEMM_BIAS_RES_F32, &p->m_hid, &m.ff1_w2, R, d, c.d_ff, w.ff1_b2, p->x, p->x, d, 0.5f, nsm, s, zz, rdev); }
     // x += W_o attn(q = W_q rope(u), k = W_k rope(u), v = W_v u), u = LN(x)   (encoder.py:485-487, 236-277)
     if (c.self_attention == 0) {
       { PROF(PC_LAYERNORM);
-        launch_ln_rope_f16(p->x, w.ln_att_g, w.ln_att_b, h->w.rope_cos, h->w.rope_sin, p->a16, p->r16, R, p->T2, dk / 2, 0, s); }
+        launch_ln_rope_f16(p->x, w.ln_att_g, w.ln_att_b, h->w.rope_cos, h->w.rope_sin, p->a16, p->r16, R, rdev, p->row_t, p->T2,
+                           dk / 2, 0, s); }
       bool merged = false;
       if (m.qkv_merged) {
         PROF(PC_GEMM_QKV);
-        merged = launch_gemm_dual_a(&p->m_r16, &p->m_a16, 2 * d, &m.w_qkv, R, 3 * d, d, w.b_qk, p->big16, 3 * d, nsm, s, zz) == 0;
+        merged = launch_gemm_dual_a(&p->m_r16, &p->m_a16, 2 * d, &m.w_qkv, R, 3 * d, d, w.b_qk, p->big16, 3 * d, nsm, s, zz, rdev) == 0;
       }
       if (!merged) {
         { PROF(PC_GEMM_QKV);
-          rc |= launch_gemm(GEMM_BIAS_F16, &p->m_r16, &m.w_qk, R, 2 * d, d, w.b_qk, nullptr, p->big16, 3 * d, 1.f, nsm, s, zz); }
+          rc |= launch_gemm(GEMM_BIAS_F16, &p->m_r16, &m.w_qk, R, 2 * d, d, w.b_qk, nullptr, p->big16, 3 * d, 1.f, nsm, s, zz, rdev); }
         { PROF(PC_GEMM_QKV);
-          rc |= launch_gemm(GEMM_BIAS_F16, &p->m_a16, &m.w_v, R, d, d, w.b_v, nullptr, p->big16 + 2 * d, 3 * d, 1.f, nsm, s, zz); }
+          rc |= launch_gemm(GEMM_BIAS_F16, &p->m_a16, &m.w_v, R, d, d, w.b_v, nullptr, p->big16 + 2 * d, 3 * d, 1.f, nsm, s, zz, rdev); }
       }
       { PROF(PC_ATTENTION);
-        rc |= launch_attention(&p->m_qkv, B > 1 ? p->len2 : nullptr, p->o16, B, p->T2, c.n_heads, dk, d, nsm, s); }
+        rc |= launch_attention(&p->m_qkv, p->plen, p->cu, p->o16, B, p->T2, c.n_heads, dk, d, nsm, s); }
     } else {
       // rel_pos (encoder.py:208-228): one projection GEMM -> [q+u | q+v | k | v], position scores inside the kernel
       { PROF(PC_LAYERNORM);
-        launch_ln_f16(p->x, w.ln_att_g, w.ln_att_b, p->a16, R, 0, s); }
+        launch_ln_f16(p->x, w.ln_att_g, w.ln_att_b, p->a16, R, rdev, 0, s); }
       { PROF(PC_GEMM_QKV);
-        rc |= launch_gemm(GEMM_BIAS_F16, &p->m_a16, &m.w_qkv_rel, R, 4 * d, d, w.b_qkv_rel, nullptr, p->big16, 4 * d, 1.f, nsm, s, zz); }
+        rc |= launch_gemm(GEMM_BIAS_F16, &p->m_a16, &m.w_qkv_rel, R, 4 * d, d, w.b_qkv_rel, nullptr, p->big16, 4 * d, 1.f, nsm, s, zz, rdev); }
       { PROF(PC_ATTENTION);
-        rc |= launch_attention_relpos(&p->m_qkv4, &m.pos_proj, B > 1 ? p->len2 : nullptr, p->o16, B, p->T2, c.n_heads, dk, d, s); }
+        rc |= launch_attention_relpos(&p->m_qkv4, &m.pos_proj, p->plen, p->cu, p->o16, B, p->T2, c.n_heads, dk, d, s); }
     }
     { PROF(PC_GEMM_PROJ);
-      rc |= launch_gemm(GEMM_BIAS_RES_F32, &p->m_o16, &m.w_o, R, d, d, w.b_o, p->x, p->x, d, 1.f, nsm, s, zz); }
+      rc |= launch_gemm(GEMM_BIAS_RES_F32, &p->m_o16, &m.w_o, R, d, d, w.b_o, p->x, p->x, d, 1.f, nsm, s, zz, rdev); }
     // x += Conv(LN(x))                                           (encoder.py:489-491, 396-409)
     { PROF(PC_LAYERNORM);
-      launch_ln_f16(p->x, w.ln_conv_g, w.ln_conv_b, p->a16, R, 0, s); }
+      launch_ln_f16(p->x, w.ln_conv_g, w.ln_conv_b, p->a16, R, rdev, 0, s); }
     { PROF(PC_GEMM_GLU);
-      rc |= launch_gemm(GEMM_BIAS_GLU_F16, &p->m_a16, &m.pw1, R, 2 * d, d, w.pw1_b, nullptr, p->g16, d, 1.f, nsm, s, zz); }
+      rc |= launch_gemm(GEMM_BIAS_GLU_F16, &p->m_a16, &m.pw1, R, 2 * d, d, w.pw1_b, nullptr, p->g16, d, 1.f, nsm, s, zz, rdev); }
     { PROF(PC_DWCONV);
       if (c.conv_norm == 0)
-        rc |= launch_dwconv_bn_silu(p->g16, w.dw_w, w.dw_b, p->len2, p->o16, B, p->T2, c.conv_kernel_size, s);
+        rc |= launch_dwconv_bn_silu(p->g16, w.dw_w, w.dw_b, p->len2, p->cu, p->plen, p->o16, B, p->T2, c.conv_kernel_size, s);
       else
-        rc |= launch_dwconv_ln_silu(p->g16, w.dw_w, w.dw_b, w.cn_g, w.cn_b, p->len2, p->o16, B, p->T2, c.conv_kernel_size, s); }
+        rc |= launch_dwconv_ln_silu(p->g16, w.dw_w, w.dw_b, w.cn_g, w.cn_b, p->len2, p->cu, p->row_b, p->row_t, rdev, p->o16, B, p->T2,
+                                    c.conv_kernel_size, s); }
     { PROF(PC_GEMM_PROJ);
-      rc |= launch_gemm(GEMM_BIAS_RES_F32, &p->m_o16, &m.pw2, R, d, d, w.pw2_b, p->x, p->x, d, 1.f, nsm, s, zz); }
+      rc |= launch_gemm(GEMM_BIAS_RES_F32, &p->m_o16, &m.pw2, R, d, d, w.pw2_b, p->x, p->x, d, 1.f, nsm, s, zz, rdev); }
     // x += 0.5 * FF2(LN(x))                                      (encoder.py:493-495)
     { PROF(PC_LAYERNORM);
-      launch_ln_f16(p->x, w.ln_ff2_g, w.ln_ff2_b, p->a16, R, 0, s); }
+      launch_ln_f16(p->x, w.ln_ff2_g, w.ln_ff2_b, p->a16, R, rdev, 0, s); }
     { PROF(PC_GEMM_FFN_UP);
-      rc |= launch_gemm(GEMM_BIAS_SILU_F16, &p->m_a16, &m.ff2_w1, R, c.d_ff, d, w.ff2_b1, nullptr, p->big16, c.d_ff, 1.f, nsm, s, zz); }
+      rc |= launch_gemm(GEMM_BIAS_SILU_F16, &p->m_a16, &m.ff2_w1, R, c.d_ff, d, w.ff2_b1, nullptr, p->big16, c.d_ff, 1.f, nsm, s, zz, rdev); }
     { PROF(PC_GEMM_FFN_DOWN);
-      rc |= launch_gemm(GEMM_BIAS_RES_F32, &p->m_hid, &m.ff2_w2, R, d, c.d_ff, w.ff2_b2, p->x, p->x, d, 0.5f, nsm, s, 0); }
+      rc |= launch_gemm(GEMM_BIAS_RES_F32, &p->m_hid, &m.ff2_w2, R, d, c.d_ff, w.ff2_b2, p->x, p->x, d, 0.5f, nsm, s, 0, rdev); }
     // x = LN_out(x) (+ next layer's first LN fused)                (encoder.py:497)
     { PROF(PC_LAYERNORM);
       if (l + 1 < L)
-        launch_ln_out_ln(p->x, w.ln_out_g, w.ln_out_b, h->layers[l + 1].ln_ff1_g, h->layers[l + 1].ln_ff1_b, p->x, p->a16, R, zz, s);
-      else
-        launch_ln_out_ln(p->x, w.ln_out_g, w.ln_out_b, nullptr, nullptr, enc, nullptr, R, zz, s); }
+        launch_ln_out_ln(p->x, w.ln_out_g, w.ln_out_b, h->layers[l + 1].ln_ff1_g, h->layers[l + 1].ln_ff1_b, p->x, p->a16, R, rdev, zz, s);
+      else   // last layer: norm_out straight into the caller's padded [B, T', d] (frames that do not exist -> 0)
+        launch_unpack_rows(p->x, w.ln_out_g, w.ln_out_b, p->cu, p->plen, enc, B, p->T2, zz, s); }
     if (rc) return fail(h, -4, "layer %d: a launch was rejected (rc=%d): %s", l, rc, cudaGetErrorString(cudaGetLastError()));
   }
   cudaMemcpyAsync(enc_len, p->len2, B * sizeof(int), cudaMemcpyDeviceToDevice, s);
@@ -707,7 +726,7 @@ int gam_test_attention(gam_handle* h, const void* qkv, const int32_t* klen, void
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   {
     PROF(PC_ATTENTION);
-    rc = launch_attention(&tq, klen, static_cast<__half*>(out), B, T, c.n_heads, c.d_model / c.n_heads, c.d_model, h->num_sms, s);
+    rc = launch_attention(&tq, klen, nullptr, static_cast<__half*>(out), B, T, c.n_heads, c.d_model / c.n_heads, c.d_model, h->num_sms, s);
   }
   if (rc) return fail(h, -4, "attention launch rejected (T=%d)", T);
   GAM_CHECK_LAUNCH(h, "test_attention");
@@ -725,10 +744,30 @@ int gam_test_attention_relpos(gam_handle* h, const void* qkv, const void* pos, c
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   {
     PROF(PC_ATTENTION);
-    rc = launch_attention_relpos(&tq, &tp, klen, static_cast<__half*>(out), B, T, c.n_heads, c.d_model / c.n_heads, c.d_model, s);
+    rc = launch_attention_relpos(&tq, &tp, klen, nullptr, static_cast<__half*>(out), B, T, c.n_heads, c.d_model / c.n_heads, c.d_model, s);
   }
   if (rc) return fail(h, -4, "rel_pos attention launch rejected (T=%d, rc=%d)", T, rc);
   GAM_CHECK_LAUNCH(h, "test_attention_relpos");
+  return 0;
+}
+
+int gam_test_attention_varlen(gam_handle* h, const void* qkv, const void* pos, const int32_t* klen, const int32_t* cu, void* out,
+                              int32_t B, int32_t T, int32_t rows, void* stream) {
+  const gam_config& c = h->cfg;
+  if (!klen || !cu || rows <= 0) return fail(h, -1, "attention_varlen: klen, cu and rows are required");
+  CUtensorMap tq, tp;
+  const uint64_t d = c.d_model, parts = pos ? 4 : 3;
+  int rc = make_tmap_2d_f16(&tq, qkv, static_cast<uint64_t>(rows), parts * d, parts * d, 128, 64);
+  if (pos) rc |= make_tmap_2d_f16(&tp, pos, 2 * kRelPosMaxT - 1, d, d, 128, 64);
+  if (rc) return fail(h, -2, "tensor map encode failed (rc=%d)", rc);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  {
+    PROF(PC_ATTENTION);
+    rc = pos ? launch_attention_relpos(&tq, &tp, klen, cu, static_cast<__half*>(out), B, T, c.n_heads, c.d_model / c.n_heads, c.d_model, s)
+             : launch_attention(&tq, klen, cu, static_cast<__half*>(out), B, T, c.n_heads, c.d_model / c.n_heads, c.d_model, h->num_sms, s);
+  }
+  if (rc) return fail(h, -4, "varlen attention launch rejected (T=%d, rc=%d)", T, rc);
+  GAM_CHECK_LAUNCH(h, "test_attention_varlen");
   return 0;
 }
 

@@ -45,10 +45,11 @@ int gemm_init() {
 }
 
 int launch_gemm(int kind, const CUtensorMap* ta, const CUtensorMap* tw, int M, int N, int K, const float* bias,
-                const float* res, void* out, int ldo, float scale, int num_sms, cudaStream_t s, int reverse) {
+                const float* res, void* out, int ldo, float scale, int num_sms, cudaStream_t s, int reverse, const int* m_dev) {
   if (N % kBN != 0 || K % kGemmBK != 0 || M <= 0) return -1;
   GemmParams p{};
   p.M = M;
+  p.m_dev = m_dev;
   p.N = N;
   p.num_m_tiles = (M + kGemmBM - 1) / kGemmBM;
   p.num_n_tiles = N / kBN;
@@ -72,10 +73,11 @@ int launch_gemm(int kind, const CUtensorMap* ta, const CUtensorMap* tw, int M, i
 // D[:, :n1] = A1 W[:n1]^T + b, D[:, n1:] = A2 W[n1:]^T + b  (fp16 out) in ONE launch of the pair kernel: more tiles per
 // launch = less wave quantisation (QK + V: 378 + 189 tiles on 74 pairs = 6 + 3 waves apart, 8 together) and one launch less.
 int launch_gemm_dual_a(const CUtensorMap* ta1, const CUtensorMap* ta2, int n1, const CUtensorMap* tw, int M, int N, int K,
-                       const float* bias, void* out, int ldo, int num_sms, cudaStream_t s, int reverse) {
+                       const float* bias, void* out, int ldo, int num_sms, cudaStream_t s, int reverse, const int* m_dev) {
   if (N % kBN != 0 || n1 % kBN != 0 || n1 <= 0 || n1 >= N || K % kGemmBK != 0 || M <= 0) return -1;
   GemmParams p{};
   p.M = M;
+  p.m_dev = m_dev;
   p.N = N;
   p.num_m_tiles = (M + kGemmBM - 1) / kGemmBM;
   p.num_n_tiles = N / kBN;
@@ -90,10 +92,12 @@ int launch_gemm_dual_a(const CUtensorMap* ta1, const CUtensorMap* ta2, int n1, c
 }
 
 int launch_gemm_conv(const CUtensorMap* ta4, const CUtensorMap* tw, int B, int T2, int C, int N, const float* bias,
-                     const int* len2, void* out, int ldo, int num_sms, cudaStream_t s) {
-  if (N % kBN != 0 || C % kGemmBK != 0) return -1;
+                     const int* len2, const int* cu, const int* plen, void* out, int ldo, int num_sms, cudaStream_t s) {
+  if (N % kBN != 0 || C % kGemmBK != 0 || (cu != nullptr) != (plen != nullptr)) return -1;
   GemmParams p{};
   p.M = 0;
+  p.conv_cu = cu;
+  p.conv_plen = plen;
   p.N = N;
   p.conv_T2 = T2;
   p.conv_tiles_per_utt = (T2 + 7) / 8;
@@ -130,9 +134,12 @@ int launch_gemm_power(const CUtensorMap* ta, const CUtensorMap* tw, int M, int N
 // k-tap / stride-2 conv1d over time-major [B, T_in, C_in] as an implicit GEMM (3-D strided TMA), K order (tap, c).
 // out rows = (b, t_out); fp16 (intermediate stage) or fp32 (last stage = encoder input) with ReLU + time mask.
 int launch_gemm_conv1d(const CUtensorMap* ta3, const CUtensorMap* tw, int B, int T_out, int C_in, int taps, int N,
-                       const float* bias, const int* len_out, void* out, int ldo, int f32_out, int num_sms, cudaStream_t s) {
-  if (N % kBN != 0 || C_in % kGemmBK != 0 || taps < 1) return -1;
+                       const float* bias, const int* len_out, const int* cu, const int* plen, void* out, int ldo, int f32_out,
+                       int num_sms, cudaStream_t s) {
+  if (N % kBN != 0 || C_in % kGemmBK != 0 || taps < 1 || (cu != nullptr) != (plen != nullptr)) return -1;
   GemmParams p{};
+  p.conv_cu = cu;
+  p.conv_plen = plen;
   p.N = N;
   p.conv_T2 = T_out;
   p.conv_tiles_per_utt = (T_out + 127) / 128;

@@ -58,9 +58,36 @@ gemm2_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const int warp_idx = threadIdx.x >> 5;
   const uint32_t rank = ptx::cluster_ctarank();
   const bool leader = rank == 0;
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles;   // num_m_tiles counts 256-row pair tiles
+  // packed rows: the row count of an A_2D product may live on the device (GemmParams::m_dev); every role derives the same
+  // tile list from it, and CTA pairs the host sized for the padded maximum simply find no tile
+  int m_rows = p.M, num_m_tiles = p.num_m_tiles;          // num_m_tiles counts 256-row pair tiles
+  if constexpr (AMODE == A_2D) {
+    if (p.m_dev != nullptr) {
+      m_rows = min(max(__ldg(p.m_dev), 0), p.M);
+      num_m_tiles = (m_rows + 255) >> 8;
+    }
+  }
+  const int num_tiles = num_m_tiles * p.num_n_tiles;
   const int pair = blockIdx.x >> 1;
   const int npairs = gridDim.x >> 1;
+  // conv modes with packed output: a 128-row block whose first frame lies past the utterance's length produces nothing,
+  // and a pair tile made of two such blocks is skipped by all three roles (same predicate, same tile list)
+  [[maybe_unused]] auto conv_tile_dead = [&](int m_pair) -> bool {
+    if constexpr (AMODE == A_2D) {
+      return false;
+    } else {
+      if (p.conv_cu == nullptr) return false;
+      constexpr int kFramesPerBlock = (AMODE == A_CONV) ? 8 : 128;
+      bool dead = true;
+#pragma unroll
+      for (int hblk = 0; hblk < 2; ++hblk) {
+        const int mb = m_pair * 2 + hblk;
+        if (mb < p.conv_num_blocks)
+          dead = dead && (mb % p.conv_tiles_per_utt) * kFramesPerBlock >= __ldg(p.conv_plen + mb / p.conv_tiles_per_utt);
+      }
+      return dead;
+    }
+  };
 
   if (warp_idx == 0 && ptx::elect_one()) {
     ptx::prefetch_tmap(&tmap_a);
@@ -91,6 +118,7 @@ gemm2_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const int tl = p.reverse ? num_tiles - 1 - tile : tile;
         const int m_pair = tl / p.num_n_tiles;
         const int n_blk = tl % p.num_n_tiles;
+        if (conv_tile_dead(m_pair)) continue;
         const int m_blk = m_pair * 2 + static_cast<int>(rank);   // this CTA's 128-row block
         const CUtensorMap* ta = (p.a1_nblks > 0 && n_blk >= p.a1_nblks) ? &tmap_a2 : &tmap_a;
         int conv_b = 0, conv_t0 = 0;
@@ -135,6 +163,9 @@ gemm2_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = pair; tile < num_tiles; tile += npairs) {
+        if constexpr (AMODE != A_2D) {
+          if (conv_tile_dead((p.reverse ? num_tiles - 1 - tile : tile) / p.num_n_tiles)) continue;
+        }
         ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         ptx::tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
@@ -173,6 +204,7 @@ gemm2_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const int tl = p.reverse ? num_tiles - 1 - tile : tile;
       const int m_pair = tl / p.num_n_tiles;
       const int n_blk = tl % p.num_n_tiles;
+      if (conv_tile_dead(m_pair)) continue;
       const int m_blk = m_pair * 2 + static_cast<int>(rank);
       // this warp's 128 bias values -> smem for broadcast reads
       if constexpr (EPI != EPI_POWER_F32) {
@@ -194,14 +226,15 @@ gemm2_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       [[maybe_unused]] int rows_live = 32;   // conv1d: how many of the warp's 32 rows are inside the valid length
       if constexpr (AMODE == A_2D) {
         warp_row0 = static_cast<long long>(m_blk) * 128 + quad * 32;
-        const long long rem = static_cast<long long>(p.M) - warp_row0;
+        const long long rem = static_cast<long long>(m_rows) - warp_row0;
         rows_valid = rem >= 32 ? 32 : (rem > 0 ? static_cast<int>(rem) : 0);
       } else if constexpr (AMODE == A_CONV1D) {
         const bool blk_ok = m_blk < p.conv_num_blocks;
         const int b = blk_ok ? m_blk / p.conv_tiles_per_utt : 0;
         const int t0 = (m_blk % p.conv_tiles_per_utt) * 128 + quad * 32;   // this warp: 32 consecutive output frames
-        warp_row0 = static_cast<long long>(b) * p.conv_T2 + t0;
-        const int tv = p.conv_T2 - t0;
+        const bool packed = p.conv_cu != nullptr;
+        warp_row0 = (packed ? static_cast<long long>(__ldg(p.conv_cu + b)) : static_cast<long long>(b) * p.conv_T2) + t0;
+        const int tv = (packed ? min(__ldg(p.conv_plen + b), p.conv_T2) : p.conv_T2) - t0;
         rows_valid = blk_ok ? (tv >= 32 ? 32 : (tv > 0 ? tv : 0)) : 0;
         const int lv = blk_ok ? p.conv_len2[b] - t0 : 0;
         rows_live = lv >= 32 ? 32 : (lv > 0 ? lv : 0);
@@ -210,8 +243,9 @@ gemm2_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const bool blk_ok = m_blk < p.conv_num_blocks;   // odd block count: the pair's second CTA idles on the last tile
         const int b = blk_ok ? m_blk / p.conv_tiles_per_utt : 0;
         const int t0 = (m_blk % p.conv_tiles_per_utt) * 8 + quad * 2;   // this warp: 2 time steps x 16 freq bins
-        warp_row0 = (static_cast<long long>(b) * p.conv_T2 + t0) * 16;
-        const int tv = p.conv_T2 - t0;
+        const bool packed = p.conv_cu != nullptr;
+        warp_row0 = ((packed ? static_cast<long long>(__ldg(p.conv_cu + b)) : static_cast<long long>(b) * p.conv_T2) + t0) * 16;
+        const int tv = (packed ? min(__ldg(p.conv_plen + b), p.conv_T2) : p.conv_T2) - t0;
         rows_valid = blk_ok ? (tv >= 2 ? 32 : (tv > 0 ? 16 : 0)) : 0;
         row_live = blk_ok && (t0 + (lane >> 4)) < p.conv_len2[b];
       }
@@ -234,7 +268,7 @@ gemm2_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           if (tile + npairs < num_tiles) {
             const int nt = p.reverse ? num_tiles - 1 - (tile + npairs) : tile + npairs;
             const long long row = (static_cast<long long>(nt / p.num_n_tiles) * 2 + static_cast<long long>(rank)) * 128 + quad * 32 + lane;
-            if (row < p.M) {
+            if (row < m_rows) {
               const float* src = p.res + static_cast<size_t>(row) * p.ldo + static_cast<size_t>(nt % p.num_n_tiles) * BN + half * 128;
 #pragma unroll
               for (int j = 0; j < 4; ++j) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + j * 32));

@@ -50,6 +50,13 @@ struct GemmParams {
   // pair kernel, A_2D only: n-tiles [0, a1_nblks) read A through tmap_a, the rest through tmap_a2 (0 = tmap_a for all).
   // Lets two GEMMs that share M, K and the output buffer but not the A operand (W_qk on rope(u), W_v on u) run as one launch.
   int a1_nblks;
+  // Packed (varlen) rows.  After the subsampling the encoder keeps only the frames that exist: utterance b owns rows
+  // cu[b] .. cu[b] + plen[b] of every activation matrix and the row count is known on the device only (lengths arrive as a
+  // device tensor and the step may be a replayed CUDA graph) -- flash_attn_varlen's cu_seqlens contract
+  // (gigaam/utils.py:103-155) applied to the whole block instead of the attention alone.
+  const int* m_dev;       // A_2D: valid rows of D read on the device (null: M); the grid is sized for M = the padded maximum
+  const int* conv_cu;     // conv modes: output row of frame (b, t) = conv_cu[b] + t (null: b * conv_T2 + t, all conv_T2 frames)
+  const int* conv_plen;   // conv modes with conv_cu: frames t < conv_plen[b] exist; row blocks past it are skipped entirely
   // A_2D only: walk the tiles from the last row block to the first.  Consecutive kernels of a layer alternate direction
   // (gam_api.cu): a consumer then starts on the rows its producer wrote LAST, which are the ones still in the 126 MB L2 --
   // read in the producer's own order, a buffer that does not fit is evicted just ahead of the reader (LRU) and every

@@ -4,8 +4,11 @@
 //   * norm_out LayerNorm fused with the next layer's first LayerNorm   (gigaam/encoder.py:497 -> :481)
 //   * masked depthwise conv (k taps) + folded eval-BatchNorm + SiLU    (gigaam/encoder.py:400-407)
 //   * masked depthwise conv + LayerNorm-over-channels + SiLU (v3 shape)
-//   * stage-length recursion of the striding subsampling               (gigaam/encoder.py:77-90)
+//   * stage-length recursion of the striding subsampling               (gigaam/encoder.py:77-90) + the packed-row plan
 // One warp owns one row of D=768 floats (24 per lane, 6 x float4, fully coalesced).
+//
+// Rows are PACKED (varlen): utterance b owns rows cu[b] .. cu[b] + plen[b] and the row count lives on the device
+// (`rows_dev`); grids are sized for the padded maximum and the surplus warps leave at once.
 #include "kernels.h"
 #include "launch.cuh"
 #include "ptx.cuh"
@@ -51,6 +54,10 @@ __device__ __forceinline__ int ln_row(int blk, int w, int rows, int reverse) {
   const int r = blk * 8 + w;
   return r >= rows ? -1 : (reverse ? rows - 1 - r : r);
 }
+// rows that exist: the device-side count when there is one (never more than the host's maximum)
+__device__ __forceinline__ int live_rows(const int* rows_dev, int rows_max) {
+  return rows_dev != nullptr ? min(max(__ldg(rows_dev), 0), rows_max) : rows_max;
+}
 
 __device__ __forceinline__ float4 ln_apply(float4 v, float mean, float rstd, float4 g, float4 b) {
   return make_float4((v.x - mean) * rstd * g.x + b.x, (v.y - mean) * rstd * g.y + b.y,
@@ -65,9 +72,9 @@ __device__ __forceinline__ uint2 pack4(float4 v) {
 // ------------------------------------------------------------------ LN -> fp16
 __global__ void __launch_bounds__(256) ln_f16_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                      const float* __restrict__ beta, __half* __restrict__ out,
-                                                     int rows, int reverse, float eps) {
+                                                     int rows_max, const int* __restrict__ rows_dev, int reverse, float eps) {
   const int lane = threadIdx.x & 31;
-  const int row = ln_row(blockIdx.x, threadIdx.x >> 5, rows, reverse);
+  const int row = ln_row(blockIdx.x, threadIdx.x >> 5, live_rows(rows_dev, rows_max), reverse);
   if (row < 0) return;
   float4 v[kVec];
   float mean, rstd;
@@ -87,12 +94,13 @@ __global__ void __launch_bounds__(256) ln_rope_f16_kernel(const float* __restric
                                                           const float* __restrict__ beta,
                                                           const float* __restrict__ rope_cos,
                                                           const float* __restrict__ rope_sin, __half* __restrict__ out_u,
-                                                          __half* __restrict__ out_r, int rows, int T, int half_dim,
-                                                          int reverse, float eps) {
+                                                          __half* __restrict__ out_r, int rows_max,
+                                                          const int* __restrict__ rows_dev, const int* __restrict__ row_t,
+                                                          int T, int half_dim, int reverse, float eps) {
   __shared__ float srow[8][kD];
   const int lane = threadIdx.x & 31;
   const int w = threadIdx.x >> 5;
-  const int row = ln_row(blockIdx.x, w, rows, reverse);
+  const int row = ln_row(blockIdx.x, w, live_rows(rows_dev, rows_max), reverse);
   if (row < 0) return;
   float4 v[kVec];
   float mean, rstd;
@@ -108,7 +116,7 @@ __global__ void __launch_bounds__(256) ln_rope_f16_kernel(const float* __restric
     s4[lane + 32 * i] = y;
   }
   __syncwarp();
-  const int t = row % T;
+  const int t = row_t != nullptr ? __ldg(row_t + row) : row % T;   // frame index inside its utterance
   const float* cs = rope_cos + static_cast<size_t>(t) * half_dim;
   const float* sn = rope_sin + static_cast<size_t>(t) * half_dim;
   // head_dim and half_dim are multiples of 4, so a float4 never straddles the rotation boundary: the partner of
@@ -134,9 +142,10 @@ __global__ void __launch_bounds__(256) ln_rope_f16_kernel(const float* __restric
 __global__ void __launch_bounds__(256) ln_out_ln_kernel(const float* __restrict__ r, const float* __restrict__ g_out,
                                                         const float* __restrict__ b_out, const float* __restrict__ g_next,
                                                         const float* __restrict__ b_next, float* __restrict__ x_out,
-                                                        __half* __restrict__ y_out, int rows, int reverse, float eps) {
+                                                        __half* __restrict__ y_out, int rows_max,
+                                                        const int* __restrict__ rows_dev, int reverse, float eps) {
   const int lane = threadIdx.x & 31;
-  const int row = ln_row(blockIdx.x, threadIdx.x >> 5, rows, reverse);
+  const int row = ln_row(blockIdx.x, threadIdx.x >> 5, live_rows(rows_dev, rows_max), reverse);
   if (row < 0) return;
   float4 v[kVec];
   float mean, rstd;
@@ -167,8 +176,42 @@ __global__ void __launch_bounds__(256) ln_out_ln_kernel(const float* __restrict_
   for (int i = 0; i < kVec; ++i) yo[lane + 32 * i] = pack4(ln_apply(v[i], mean, rstd, gn[lane + 32 * i], bn[lane + 32 * i]));
 }
 
+// ------------------------------------------------------------------ packed rows -> the caller's padded [B, T, 768] fp32
+// out[b, t] = LN(x[cu[b] + t]) (gamma != null: the last layer's norm_out, gigaam/encoder.py:497) or x[cu[b] + t] itself
+// (pre_encode output); frames t >= plen[b] do not exist in the packed stream and are written as zeros.
+__global__ void __launch_bounds__(256) unpack_rows_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, const int* __restrict__ cu,
+                                                          const int* __restrict__ plen, float* __restrict__ out, int B, int T,
+                                                          int reverse, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int orow = ln_row(blockIdx.x, threadIdx.x >> 5, B * T, reverse);
+  if (orow < 0) return;
+  const int b = orow / T, t = orow - b * T;
+  float4* o = reinterpret_cast<float4*>(out + static_cast<size_t>(orow) * kD);
+  if (t >= min(__ldg(plen + b), T)) {
+#pragma unroll
+    for (int i = 0; i < kVec; ++i) o[lane + 32 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
+  const float* src = x + (static_cast<size_t>(__ldg(cu + b)) + t) * kD;
+  float4 v[kVec];
+  if (gamma != nullptr) {
+    float mean, rstd;
+    load_row_stats(src, lane, v, mean, rstd, eps);
+    const float4* g4 = reinterpret_cast<const float4*>(gamma);
+    const float4* b4 = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+    for (int i = 0; i < kVec; ++i) o[lane + 32 * i] = ln_apply(v[i], mean, rstd, g4[lane + 32 * i], b4[lane + 32 * i]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < kVec; ++i) o[lane + 32 * i] = reinterpret_cast<const float4*>(src)[lane + 32 * i];
+  }
+}
+
 // ------------------------------------------------------------------ depthwise conv (+ folded BN) + SiLU
-// g: [B, T, 768] fp16 (GLU output, NOT yet pad-masked: masked here on load, gigaam/encoder.py:400-401)
+// g: packed rows x 768 fp16 (GLU output, NOT yet pad-masked: masked here on load, gigaam/encoder.py:400-401); utterance b
+// starts at row cu[b] and owns plen[b] rows (cu == null: row b*T, T rows); frames t >= len[b] read as zero (len < plen only
+// for a batch of one, whose padded frames stay in the stream because the reference attends to them).
 // w: [768, KW] fp32, b: [768] fp32 with eval BatchNorm folded in.  out = silu(conv) fp16.
 // block = (channel tile of 128, time tile of 64, b); thread = 2 channels x 16 time steps.
 constexpr int kDwTT = 32;          // time steps per block
@@ -178,6 +221,7 @@ constexpr int kDwPerThread = 8;    // consecutive outputs per thread (x 2 channe
 template <int KW>
 __global__ void __launch_bounds__(256) dwconv_bn_silu_kernel(const __half* __restrict__ g, const float* __restrict__ w,
                                                              const float* __restrict__ bias, const int* __restrict__ len,
+                                                             const int* __restrict__ cu, const int* __restrict__ plen,
                                                              __half* __restrict__ out, int T) {
   constexpr int kHalo = (KW - 1) / 2;
   constexpr int kRows = kDwTT + KW - 1;
@@ -186,7 +230,10 @@ __global__ void __launch_bounds__(256) dwconv_bn_silu_kernel(const __half* __res
   const int t0 = blockIdx.y * kDwTT;
   const int b = blockIdx.z;
   const int L = min(len[b], T);
-  const __half* gb = g + static_cast<size_t>(b) * T * kD;
+  const int P = cu != nullptr ? min(__ldg(plen + b), T) : T;   // frames of this utterance that exist
+  if (t0 >= P) return;
+  const size_t base = cu != nullptr ? static_cast<size_t>(__ldg(cu + b)) : static_cast<size_t>(b) * T;
+  const __half* gb = g + base * kD;
   // input tile: 16-byte loads, one 256-byte row segment per 16 threads; padded frames / halo -> 0
   for (int i = threadIdx.x; i < kRows * (kDwCT / 8); i += blockDim.x) {
     const int rr = i / (kDwCT / 8), c8 = i % (kDwCT / 8);
@@ -218,11 +265,11 @@ __global__ void __launch_bounds__(256) dwconv_bn_silu_kernel(const __half* __res
       a1[o] = fmaf(wk.y, x[o + k].y, a1[o]);
     }
   }
-  __half* ob = out + static_cast<size_t>(b) * T * kD;
+  __half* ob = out + base * kD;
 #pragma unroll
   for (int o = 0; o < kDwPerThread; ++o) {
     const int t = t0 + rbase + o;
-    if (t < T) {
+    if (t < P) {
       // silu(a) = 0.5 a (1 + tanh(0.5 a)): one MUFU, no division
       const float h0 = 0.5f * a0[o], h1 = 0.5f * a1[o];
       float t0v, t1v;
@@ -239,12 +286,16 @@ template <int KW>
 __global__ void __launch_bounds__(256) dwconv_ln_silu_kernel(const __half* __restrict__ g, const float* __restrict__ w,
                                                              const float* __restrict__ bias, const float* __restrict__ gamma,
                                                              const float* __restrict__ beta, const int* __restrict__ len,
-                                                             __half* __restrict__ out, int T, int rows, float eps) {
+                                                             const int* __restrict__ cu, const int* __restrict__ row_b,
+                                                             const int* __restrict__ row_t, const int* __restrict__ rows_dev,
+                                                             __half* __restrict__ out, int T, int rows_max, float eps) {
   constexpr int kHalo = (KW - 1) / 2;
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  const int b = row / T, t = row % T;
+  if (row >= live_rows(rows_dev, rows_max)) return;
+  const int b = cu != nullptr ? __ldg(row_b + row) : row / T;
+  const int t = cu != nullptr ? __ldg(row_t + row) : row % T;
+  const size_t base = cu != nullptr ? static_cast<size_t>(__ldg(cu + b)) : static_cast<size_t>(b) * T;
   const int L = min(len[b], T);
   float acc[24];
 #pragma unroll
@@ -252,7 +303,7 @@ __global__ void __launch_bounds__(256) dwconv_ln_silu_kernel(const __half* __res
   for (int k = 0; k < KW; ++k) {
     const int tt = t + k - kHalo;
     if (tt < 0 || tt >= L) continue;
-    const __half2* src = reinterpret_cast<const __half2*>(g + (static_cast<size_t>(b) * T + tt) * kD + lane * 24);
+    const __half2* src = reinterpret_cast<const __half2*>(g + (base + tt) * kD + lane * 24);
 #pragma unroll
     for (int i = 0; i < 12; ++i) {
       const float2 x = __half22float2(src[i]);
@@ -280,53 +331,130 @@ __global__ void __launch_bounds__(256) dwconv_ln_silu_kernel(const __half* __res
   }
 }
 
-// ------------------------------------------------------------------ subsampling length recursion
-// len_k = floor((len_{k-1} + 2p - k) / 2 + 1), computed in float like the reference (encoder.py:86-90)
-__global__ void sub_lengths_kernel(const long long* __restrict__ mel_len, int B, int pad2_minus_k, int max_T0, int* __restrict__ len0,
-                                   int* __restrict__ len1, int* __restrict__ len2) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
-  float l = static_cast<float>(mel_len[b]);
-  len0[b] = static_cast<int>(min(mel_len[b], static_cast<long long>(max_T0)));
-  l = floorf((l + pad2_minus_k) / 2.0f + 1.0f);
-  len1[b] = static_cast<int>(l);
-  l = floorf((l + pad2_minus_k) / 2.0f + 1.0f);
-  len2[b] = static_cast<int>(l);
+// ------------------------------------------------------------------ subsampling length recursion + packed-row plan
+// len_k = floor((len_{k-1} + 2p - k) / 2 + 1), computed in float like the reference (encoder.py:86-90).
+// plen[b] = frames of utterance b kept in the packed stream = len2[b]; a batch of ONE keeps all T2 frames because the
+// reference builds no attention mask for it (encoder.py:621-625) and its padded frames are attended to.
+// cu = exclusive prefix sum of plen ([B + 1]; cu[B] = rows_dev[0] = packed row count); run1[b] = how many stage-1 frames
+// of the conv2d subsampling the stage-2 conv of the kept frames can touch (stage 1 writes exactly those).
+// One block; B is walked in chunks of blockDim.x with a carried prefix.
+__global__ void __launch_bounds__(1024) pack_plan_kernel(const long long* __restrict__ mel_len, int B, int pad2_minus_k, int max_T0,
+                                                         int T1, int T2, int* __restrict__ len0, int* __restrict__ len1,
+                                                         int* __restrict__ len2, int* __restrict__ plen, int* __restrict__ run1,
+                                                         int* __restrict__ cu, int* __restrict__ rows_dev) {
+  __shared__ int warp_tot[32];
+  __shared__ int carry_s;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int b0 = 0; b0 < B; b0 += blockDim.x) {
+    const int b = b0 + threadIdx.x;
+    int pl = 0;
+    if (b < B) {
+      float l = static_cast<float>(mel_len[b]);
+      len0[b] = static_cast<int>(min(mel_len[b], static_cast<long long>(max_T0)));
+      l = floorf((l + pad2_minus_k) / 2.0f + 1.0f);
+      const int l1 = static_cast<int>(l);
+      len1[b] = l1;
+      l = floorf((l + pad2_minus_k) / 2.0f + 1.0f);
+      const int l2 = static_cast<int>(l);
+      len2[b] = l2;
+      pl = B > 1 ? min(max(l2, 0), T2) : T2;
+      plen[b] = pl;
+      // conv2d: a kept stage-2 frame t2 reads stage-1 frames 2 t2 - 1 .. 2 t2 + 1 and stage 2 works in blocks of 8 frames, so
+      // every stage-1 frame below 2 * roundup8(pl) must be defined (zeros past len1 included); nothing above it is read
+      // by a block that stores anything
+      run1[b] = B > 1 ? min(T1, 2 * ((pl + 7) / 8 * 8) + 2) : T1;
+    }
+    int v = pl;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int n = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += n;
+    }
+    if (lane == 31) warp_tot[w] = v;
+    __syncthreads();
+    if (w == 0) {
+      int tv = lane < nw ? warp_tot[lane] : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int n = __shfl_up_sync(0xffffffffu, tv, o);
+        if (lane >= o) tv += n;
+      }
+      warp_tot[lane] = tv;   // inclusive totals of the warps
+    }
+    __syncthreads();
+    const int carry = carry_s;
+    const int incl = carry + v + (w > 0 ? warp_tot[w - 1] : 0);
+    if (b < B) cu[b] = incl - pl;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry_s = incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    cu[B] = carry_s;
+    rows_dev[0] = carry_s;
+  }
+}
+
+// row -> (utterance, frame) of the packed stream, for the kernels that walk rows but need the position (RoPE, conv halo)
+__global__ void row_map_kernel(const int* __restrict__ cu, const int* __restrict__ plen, int T, int* __restrict__ row_b,
+                               int* __restrict__ row_t) {
+  const int b = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < min(plen[b], T)) {
+    const int r = cu[b] + t;
+    row_b[r] = b;
+    row_t[r] = t;
+  }
 }
 
 }  // namespace
 
 // ------------------------------------------------------------------ launchers
-void launch_ln_f16(const float* x, const float* g, const float* b, __half* out, int rows, int reverse, cudaStream_t s) {
-  launch_k(ln_f16_kernel, dim3((rows + 7) / 8), dim3(256), 0, s, x, g, b, out, rows, reverse, 1e-5f);
+void launch_ln_f16(const float* x, const float* g, const float* b, __half* out, int rows, const int* rows_dev, int reverse,
+                   cudaStream_t s) {
+  launch_k(ln_f16_kernel, dim3((rows + 7) / 8), dim3(256), 0, s, x, g, b, out, rows, rows_dev, reverse, 1e-5f);
 }
 void launch_ln_rope_f16(const float* x, const float* g, const float* b, const float* rc, const float* rs, __half* out_u,
-                        __half* out_r, int rows, int T, int half_dim, int reverse, cudaStream_t s) {
-  launch_k(ln_rope_f16_kernel, dim3((rows + 7) / 8), dim3(256), 0, s, x, g, b, rc, rs, out_u, out_r, rows, T, half_dim, reverse, 1e-5f);
+                        __half* out_r, int rows, const int* rows_dev, const int* row_t, int T, int half_dim, int reverse,
+                        cudaStream_t s) {
+  launch_k(ln_rope_f16_kernel, dim3((rows + 7) / 8), dim3(256), 0, s, x, g, b, rc, rs, out_u, out_r, rows, rows_dev, row_t, T,
+           half_dim, reverse, 1e-5f);
 }
 void launch_ln_out_ln(const float* r, const float* g_out, const float* b_out, const float* g_next, const float* b_next,
-                      float* x_out, __half* y_out, int rows, int reverse, cudaStream_t s) {
-  launch_k(ln_out_ln_kernel, dim3((rows + 7) / 8), dim3(256), 0, s, r, g_out, b_out, g_next, b_next, x_out, y_out, rows, reverse, 1e-5f);
+                      float* x_out, __half* y_out, int rows, const int* rows_dev, int reverse, cudaStream_t s) {
+  launch_k(ln_out_ln_kernel, dim3((rows + 7) / 8), dim3(256), 0, s, r, g_out, b_out, g_next, b_next, x_out, y_out, rows, rows_dev,
+           reverse, 1e-5f);
 }
-int launch_dwconv_bn_silu(const __half* g, const float* w, const float* bias, const int* len, __half* out, int B, int T,
-                          int kw, cudaStream_t s) {
+void launch_unpack_rows(const float* x, const float* gamma, const float* beta, const int* cu, const int* plen, float* out, int B,
+                        int T, int reverse, cudaStream_t s) {
+  launch_k(unpack_rows_kernel, dim3((B * T + 7) / 8), dim3(256), 0, s, x, gamma, beta, cu, plen, out, B, T, reverse, 1e-5f);
+}
+int launch_dwconv_bn_silu(const __half* g, const float* w, const float* bias, const int* len, const int* cu, const int* plen,
+                          __half* out, int B, int T, int kw, cudaStream_t s) {
   dim3 grid(kD / kDwCT, (T + kDwTT - 1) / kDwTT, B);
-  if (kw == 31) launch_k(dwconv_bn_silu_kernel<31>, grid, dim3(256), 0, s, g, w, bias, len, out, T);
-  else if (kw == 5) launch_k(dwconv_bn_silu_kernel<5>, grid, dim3(256), 0, s, g, w, bias, len, out, T);
+  if (kw == 31) launch_k(dwconv_bn_silu_kernel<31>, grid, dim3(256), 0, s, g, w, bias, len, cu, plen, out, T);
+  else if (kw == 5) launch_k(dwconv_bn_silu_kernel<5>, grid, dim3(256), 0, s, g, w, bias, len, cu, plen, out, T);
   else return -1;
   return 0;
 }
 int launch_dwconv_ln_silu(const __half* g, const float* w, const float* bias, const float* gamma, const float* beta,
-                          const int* len, __half* out, int B, int T, int kw, cudaStream_t s) {
+                          const int* len, const int* cu, const int* row_b, const int* row_t, const int* rows_dev, __half* out,
+                          int B, int T, int kw, cudaStream_t s) {
   const int rows = B * T;
-  if (kw == 5) dwconv_ln_silu_kernel<5><<<(rows + 7) / 8, 256, 0, s>>>(g, w, bias, gamma, beta, len, out, T, rows, 1e-5f);
-  else if (kw == 31) dwconv_ln_silu_kernel<31><<<(rows + 7) / 8, 256, 0, s>>>(g, w, bias, gamma, beta, len, out, T, rows, 1e-5f);
+  if (kw == 5)
+    dwconv_ln_silu_kernel<5><<<(rows + 7) / 8, 256, 0, s>>>(g, w, bias, gamma, beta, len, cu, row_b, row_t, rows_dev, out, T, rows, 1e-5f);
+  else if (kw == 31)
+    dwconv_ln_silu_kernel<31><<<(rows + 7) / 8, 256, 0, s>>>(g, w, bias, gamma, beta, len, cu, row_b, row_t, rows_dev, out, T, rows, 1e-5f);
   else return -1;
   return 0;
 }
-void launch_sub_lengths(const long long* mel_len, int B, int pad2_minus_k, int max_T0, int* len0, int* len1, int* len2,
-                        cudaStream_t s) {
-  sub_lengths_kernel<<<(B + 127) / 128, 128, 0, s>>>(mel_len, B, pad2_minus_k, max_T0, len0, len1, len2);
+void launch_pack_plan(const long long* mel_len, int B, int pad2_minus_k, int max_T0, int T1, int T2, int* len0, int* len1,
+                      int* len2, int* plen, int* run1, int* cu, int* rows_dev, int* row_b, int* row_t, cudaStream_t s) {
+  const int threads = B >= 1024 ? 1024 : ((B + 31) / 32 * 32);
+  pack_plan_kernel<<<1, threads, 0, s>>>(mel_len, B, pad2_minus_k, max_T0, T1, T2, len0, len1, len2, plen, run1, cu, rows_dev);
+  row_map_kernel<<<dim3((T2 + 255) / 256, B), 256, 0, s>>>(cu, plen, T2, row_b, row_t);
 }
 
 }  // namespace gam

@@ -123,6 +123,9 @@ class _WorkspaceCache:
     def peek(self, key) -> Optional[Tensor]:
         return self._d.get(key)
 
+    def tensors(self) -> List[Tensor]:
+        return list(self._d.values())
+
     def __len__(self):
         return len(self._d)
 

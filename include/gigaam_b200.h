@@ -198,6 +198,12 @@ int gam_test_attention(gam_handle* h, const void* qkv, const int32_t* klen, void
 /* rel_pos variant: qkv f16 [B*T, 4*d_model] = [q+u | q+v | k | v]; pos f16 [2*GAM_REL_POS_MAX_T-1, d_model] */
 int gam_test_attention_relpos(gam_handle* h, const void* qkv, const void* pos, const int32_t* klen, void* out, int32_t B,
                               int32_t T, void* stream);
+/* packed-row (varlen) form of the two calls above, the one gam_encode uses: qkv f16 [rows, 3*d_model] (pos == NULL, rotary)
+ * or [rows, 4*d_model] (pos != NULL, rel_pos); utterance b owns rows cu[b] .. cu[b] + klen[b] (cu: i32 [B + 1], klen: i32
+ * [B], klen[b] <= T) -> out f16 [rows, d_model]; rows that belong to no utterance are left untouched.  This is the
+ * cu_seqlens contract of flash_attn_varlen_func in gigaam/utils.py:103-155 (apply_masked_flash_attn). */
+int gam_test_attention_varlen(gam_handle* h, const void* qkv, const void* pos, const int32_t* klen, const int32_t* cu, void* out,
+                              int32_t B, int32_t T, int32_t rows, void* stream);
 /* number of kernels this handle has launched so far (bench.py's gpu_launches) */
 int64_t gam_launch_count(const gam_handle* h);
 

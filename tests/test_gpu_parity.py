@@ -826,3 +826,121 @@ def test_transcribe_longform_equals_per_segment_transcribe(dev, v2_ctc_ckpt):
     res = model.transcribe_longform(long_wav[0])
     assert len(res) >= 3 and res.segments[0].start == 0.0 and res.segments[-1].end == pytest.approx(50.0)
     assert all(s.end - s.start <= 22.0 + 1e-6 for s in res) and isinstance(res.text, str)
+
+
+# ------------------------------------------------------------------------------------------ varlen (packed-row) execution, SURVEY 8 a19
+def _pack(x_btc, lens):
+    return torch.cat([x_btc[b, :n] for b, n in enumerate(lens)], 0)
+
+
+@pytest.mark.parametrize("relpos", [False, True])
+@pytest.mark.parametrize("T,lens", [(251, [251, 97, 1, 0, 128, 129, 200]), (128, [5, 128, 64]), (751, [751, 129, 640, 300]),
+                                    (376, [0, 376, 257, 31])])
+def test_attention_varlen_packed_rows(request, dev, relpos, T, lens):
+    """The cu_seqlens contract of apply_masked_flash_attn (gigaam/utils.py:103-155): q / k / v rows of the utterances lie
+    back to back, every utterance attends to its own frames only, nothing is computed for frames that do not exist.  The
+    rows behind the last utterance are poisoned with NaN: a tile that reaches past the stream must not let them in."""
+    from gigaam_b200 import _lib
+    eng = request.getfixturevalue("eng_v1" if relpos else "eng_ctc")
+    B, d, H, dk, L = len(lens), 768, 16, 48, _lib.REL_POS_MAX_T
+    parts = 4 if relpos else 3
+    g = torch.Generator().manual_seed(T + 17 * B + relpos)
+    x = torch.randn(B, T, parts * d, generator=g).half()
+    rows = sum(lens)
+    qkv = torch.full((rows + 300, parts * d), float("nan"), dtype=torch.float16)
+    qkv[:rows] = _pack(x, lens)
+    qkv = qkv.to(dev)
+    pos = torch.randn(2 * L - 1, d, generator=g).half().to(dev)
+    out = torch.full((rows + 300, d), 7.0, dtype=torch.float16, device=dev)
+    klen = torch.tensor(lens, dtype=torch.int32, device=dev)
+    cu = torch.tensor([0] + list(np.cumsum(lens)), dtype=torch.int32, device=dev)
+    rc = eng.lib.gam_test_attention_varlen(eng.handle, qkv.data_ptr(), pos.data_ptr() if relpos else None, klen.data_ptr(),
+                                           cu.data_ptr(), out.data_ptr(), B, T, rows + 300, _stream())
+    torch.cuda.synchronize()
+    assert rc == 0, eng.lib.gam_last_error(eng.handle)
+    assert torch.isfinite(out).all()
+    assert bool((out[rows:] == 7.0).all())                 # nothing stored behind the stream
+    for b, n in enumerate(lens):
+        if n == 0:
+            continue
+        xb = x[b, :n].float().to(dev).view(n, parts, H, dk)
+        if relpos:
+            qu, qv, k, v = (xb[:, i].transpose(0, 1) for i in range(4))
+            p = pos.float()[L - n: L + n - 1].view(2 * n - 1, H, dk).transpose(0, 1)
+            bd = qv @ p.transpose(-1, -2)
+            bd = F.pad(bd, (1, 0)).view(H, -1, n)[:, 1:].reshape(H, n, 2 * n - 1)[..., :n]      # rel_shift, encoder.py:202-206
+            sc = (qu @ k.transpose(-1, -2) + bd) / dk ** 0.5
+        else:
+            q, k, v = (xb[:, i].transpose(0, 1) for i in range(3))
+            sc = q @ k.transpose(-1, -2) / dk ** 0.5
+        want = (torch.softmax(sc, -1) @ v).transpose(0, 1).reshape(n, d)
+        got = out[int(cu[b]): int(cu[b]) + n].float()
+        assert rel(got, want) < 1e-3, (b, n)
+
+
+@pytest.mark.parametrize("which", ["v2_ctc", "v3_e2e_rnnt", "v1_ctc"])
+def test_varlen_ragged_batch_against_oracle(request, dev, which):
+    """A strongly ragged batch (10 s down to a single encoder frame) through load_model(...) in the benchmarked fp16 mode vs
+    the oracle on the valid frames, for the three encoder shapes (conv2d + BatchNorm + rotary; conv1d + LayerNorm;
+    rel_pos).  Only sum(len) rows run through the blocks; frames that do not exist come back as zeros; a second call
+    with the scratch memory poisoned with NaN gives bit-identical results (nothing stale is ever read)."""
+    ck = {"v2_ctc": "v2_ctc_ckpt", "v3_e2e_rnnt": "v3_ckpt", "v1_ctc": "v1_ctc_ckpt"}[which]
+    ckpt = request.getfixturevalue(ck)
+    model = gigaam.load_model(which, device=dev, checkpoint=ckpt)
+    secs = [10.0, 0.06, 3.3, 7.77, 0.5, 10.0, 1.29, 5.12]
+    wav, _ = synthetic.synthetic_audio(len(secs), 10.0, seed=4321)
+    wav_len = torch.tensor([int(s * 16000) for s in secs])
+    for b, n in enumerate(wav_len.tolist()):
+        wav[b, n:] = 0.0
+    enc, enc_len, enc_o, len_o, _ = _encoder_parity(model, ckpt, wav, wav_len, dev)
+    assert int(len_o.min()) <= 2 and int(len_o.max()) >= 250
+    pad = torch.arange(enc.shape[2], device=dev)[None, :] >= enc_len[:, None]
+    assert float(enc.transpose(1, 2)[pad].abs().max()) == 0.0
+    eng = model._get_engine()
+    for cache in (eng._ws_enc, eng._ws_mel, eng._ws_dec):
+        for t in cache.tensors():
+            t.view(torch.float16).fill_(float("nan"))
+    enc2, _ = model(wav.to(dev), wav_len.to(dev))
+    assert torch.equal(enc, enc2)
+
+
+def test_varlen_rows_scale_with_audio_not_with_padding(dev, v2_ctc_ckpt):
+    """Size-independent property at the BASELINE config-2 shape: 64 utterances of which 48 are 1 s long inside a 10 s
+    buffer.  Each utterance equals its run inside a batch of its own kind (lengths alone decide the result, padding does
+    not), and the step is much cheaper than the 64 x 10 s one because only the existing frames are computed."""
+    model = gigaam.load_model("v2_ctc", device=dev, checkpoint=v2_ctc_ckpt)
+    wav, _ = synthetic.synthetic_audio(64, 10.0, seed=99)
+    full_len = torch.full((64,), 160000)
+    rag_len = full_len.clone()
+    rag_len[16:] = 16000
+    wav_r = wav.clone()
+    wav_r[16:, 16000:] = 0.0
+    eng = model._get_engine()
+    mel = eng.logmel(wav_r.to(dev))
+    mel_len = (rag_len // 160 + 1).to(dev)
+    m1 = int(mel_len[16])
+    enc_r, len_r = eng.encode(mel, mel_len)
+    enc_s, len_s = eng.encode(mel[16:, :, :m1].contiguous(), mel_len[16:])       # the short ones alone: no padded frame anywhere
+    n = int(len_s[0])
+    assert torch.equal(len_r[16:], len_s) and n == 26
+    assert rel(enc_r[16:, :n], enc_s[:, :n]) < 1e-5 or float((enc_r[16:, :n] - enc_s[:, :n]).abs().max()) < 1e-3
+    assert float(enc_r[16:, n:].abs().max()) == 0.0
+    enc_f, _ = eng.encode(mel[:16].contiguous(), mel_len[:16])                    # the long ones alone
+    assert rel(enc_r[:16], enc_f) < 1e-5 or float((enc_r[:16] - enc_f).abs().max()) < 1e-3
+
+    def timed(w, l):
+        w, l = w.to(dev), l.to(dev)
+        for _ in range(2):
+            model(w, l)
+        torch.cuda.synchronize()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(5):
+            model(w, l)
+        t1.record()
+        torch.cuda.synchronize()
+        return t0.elapsed_time(t1) / 5
+    t_full, t_rag = timed(wav, full_len), timed(wav_r, rag_len)
+    frac = float(rag_len.sum()) / float(full_len.sum())
+    print(f"64 x 10 s: {t_full:.2f} ms; 16 x 10 s + 48 x 1 s in the same buffer ({frac:.2f} of the audio): {t_rag:.2f} ms")
+    assert t_rag < 0.6 * t_full
