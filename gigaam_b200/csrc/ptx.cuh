@@ -201,6 +201,17 @@ __device__ __forceinline__ void tmem_st_wait() {
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
+// Per-warpgroup register budget (all four warps of a warpgroup execute it): the data-movement warpgroup gives registers
+// back to the CTA's pool, the math warpgroups take them.  ptxas allocates the code behind each to the stated limit.
+template <int kRegs>
+__device__ __forceinline__ void setmaxnreg_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs));
+}
+template <int kRegs>
+__device__ __forceinline__ void setmaxnreg_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs));
+}
+
 // ---------------------------------------------------------------- CTA pairs (cta_group::2) and clusters
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
