@@ -12,24 +12,32 @@
 // layout is the padded [B, T] one (unit tests): row b*T, every query row stored.  The rows of the last key block past
 // klen are zeroed in shared memory before P.V: their P is 0, but 0 x (stale inf / NaN bits) would not be.
 //
-// ONE kernel, one sweep.  At head_dim 48 the tensor work of a 128 x 128 score block is ~150 cycles, reading the block
-// out of tensor memory (64 B / cycle / SM) is ~1000 and its exponentials (16 / cycle / SM) are ~1000: the kernel is
-// built around reading every score ONCE.  A softmax thread (one per query row) pulls its 128 scores of a key block into
-// registers with four tcgen05.ld, releases the block at once (the tensor core computes the next S while this one is
-// exponentiated), and runs an online softmax on the registers:
-//   * running maximum with a LAZY update: the reference point moves only when a block maximum exceeds it by more than
-//     2^8 (P then stays <= 256, far inside fp16); the first block sets it exactly.  Moving it rescales the O
-//     accumulator in tensor memory, which happens after the previous P.V has retired and is rare on real score rows;
+// ONE kernel, one sweep: every score is read out of tensor memory once.  A softmax thread (one per query row) pulls its
+// 128 scores of a key block into registers with four tcgen05.ld, releases the block at once (the tensor core computes
+// the next S while this one is exponentiated), and runs an online softmax on the registers:
+//   * LAZY reference point: exact block maximum on the first block; afterwards it moves only when a block maximum exceeds
+//     it by more than 2^8 (P then stays <= 256, far inside fp16).  Moving it rescales the O accumulator in tensor memory
+//     (after the previous P.V has retired); on real score rows that is rare;
+//   * the softmax denominator comes from the tensor core: column dk of every V tile is set to 1.0 in shared memory, so
+//     O[:, dk] accumulates the row sum of exactly the fp16 P that P.V used (P.V multiplies all 64 columns of the tile
+//     anyway) and follows every rescaling of O by construction;
 //   * P goes back to tensor memory as packed fp16 (tcgen05.st) into its own 64 columns and O += P V runs as a TS-mode
 //     tcgen05.mma with V straight from its [key, d] layout (MN-major B).  S, P and O have separate columns, so S of
 //     block k+1, the softmax of block k and P.V of block k-1 are in flight together.
-// K / V blocks are 128 keys x 64 columns (SWIZZLE_128B; the 16 columns past the 48 real ones belong to the next head
-// and are never multiplied: QK^T runs K = 3 x 16 and the 16 extra output columns of P.V are dropped).
+// K / V blocks are 128 keys x 64 columns (SWIZZLE_128B; the 16 columns past the 48 real ones belong to the next head:
+// QK^T runs K = 3 x 16 and never touches them; of the 16 extra output columns of P.V, column dk is the row sum and the
+// other 15 are dropped).
 //
 // Persistent CTA per SM over (utterance, head) items; two query-tile streams per CTA (a softmax warpgroup + an MMA
 // issuer warp + 256 TMEM columns each: S [0,128) | P [128,192) | O [192,256)) take alternate query tiles of the item.
 // The item's K / V blocks are resident in shared memory and shared by both streams; with up to 3 key blocks (T' <= 384)
-// a second set of K / V buffers lets the producer fetch the next item while this one is computed.
+// a second set of K / V buffers lets the producer fetch the next item while this one is computed.  Output rows leave
+// through a per-warp staging tile as runs of whole rows (see the epilogue).
+//
+// Measured (tools/attn_probe.py, profiles/r2n_attn_probe.txt): 55 us per launch at the c2 shape (64 x 251; the two-sweep
+// kernels it replaces: 56), 61 us at c3 (32 x 376; before: 89), 139 us at 32 x 626 (before: 191).  Moving a quarter or a half
+// of the exponentials to the FMA pipe (Cody-Waite + cubic) changed nothing: the softmax warps are bound by the latency of
+// their serial block chain (ld -> max -> exp -> st -> P.V -> O), not by MUFU or issue throughput.
 #include "kernels.h"
 #include "launch.cuh"
 #include "ptx.cuh"
@@ -42,6 +50,9 @@ constexpr int kTileBytes = 128 * 128;  // 128 rows x 64 fp16
 constexpr int kThreads = 384;          // warp 0 TMA, 1 / 2 MMA issuers, 3 TMEM owner, 4-7 / 8-11 softmax warpgroups
 constexpr uint32_t kPCol = 128, kOCol = 192;
 constexpr float kLazyLog2 = 8.0f;      // the softmax reference point trails the running maximum by at most 2^8
+constexpr int kBarBytes = 512;         // mbarriers + TMEM base slot
+constexpr int kStagePitch = 112;       // bytes per staged output row (96 used): conflict-free 16-byte accesses
+constexpr int kStageBytes = 8 * 32 * kStagePitch;   // one 32-row staging tile per softmax warp
 
 __device__ __forceinline__ float ex2(float x) {
   float y;
@@ -87,7 +98,8 @@ __device__ __forceinline__ void zero_v_tail(uint8_t* v_tile, int r, int valid_ro
 
 struct AttnParams {
   int T, nkb, B, H;
-  int ring;          // K / V buffer sets (2 when they fit: T' <= 384)
+  int ring;          // K / V buffer sets (2 when they fit)
+  int stage;         // output rows go through a shared-memory staging tile (whenever it fits)
   const int* klen;
   const int* cu;
   __half* out;
@@ -117,6 +129,7 @@ __global__ void __launch_bounds__(kThreads, 1) attention_kernel(const __grid_con
   uint64_t* p_empty = q_full + 10;
   uint64_t* o_empty = q_full + 12;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_full + 14);
+  uint8_t* sStage = reinterpret_cast<uint8_t*>(bars) + kBarBytes;
 
   const int warp_idx = threadIdx.x >> 5;
   const int n_items = p.B * p.H;
@@ -260,20 +273,25 @@ __global__ void __launch_bounds__(kThreads, 1) attention_kernel(const __grid_con
     const int lane = threadIdx.x & 31;
     const int r = quad * 32 + lane;
     const uint32_t t_s = tmem_base + wg * 256 + (static_cast<uint32_t>(quad * 32) << 16);
+    uint8_t* stage_w = sStage + (warp_idx - 4) * (32 * kStagePitch);
+    const int item_stride = gridDim.x;
     int it = 0;
     uint32_t n_s = 0;   // S blocks consumed by this stream so far
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      const int b = item / p.H, h = item % p.H;
-      const ItemGeom g = item_geom(p.klen, p.cu, b, p.T, nkb);
+    // the geometry of the NEXT item (two dependent global loads) is fetched while this one is computed
+    int item = blockIdx.x;
+    ItemGeom g_next = item_geom(p.klen, p.cu, min(item, n_items - 1) / p.H, p.T, nkb);
+    for (; item < n_items; item += item_stride) {
+      const int h = item % p.H;
+      const ItemGeom g = g_next;
+      g_next = item_geom(p.klen, p.cu, min(item + item_stride, n_items - 1) / p.H, p.T, nkb);
       if (g.nq == 0) continue;
       const int set = it % p.ring;
       ++it;
       uint8_t* sV = smem + set * set_bytes + nkb * kTileBytes;
       for (int qt = wg; qt < g.nq; qt += 2) {
         float mc = 0.f;    // softmax reference point x scale (log2 domain)
-        float sum = 0.f;
         for (int kb = 0; kb < g.nk; ++kb, ++n_s) {
-          const int nvalid = min(g.klen - kb * 128, 128);
+          const int nvalid = max(min(g.klen - kb * 128, 128), 0);
           ptx::mbar_wait(&s_full[wg], n_s & 1);
           ptx::tc_fence_after();
           uint32_t s[128];
@@ -281,13 +299,21 @@ __global__ void __launch_bounds__(kThreads, 1) attention_kernel(const __grid_con
           ptx::tmem_ld_32x32b_x32(t_s + 32, s + 32);
           ptx::tmem_ld_32x32b_x32(t_s + 64, s + 64);
           ptx::tmem_ld_32x32b_x32(t_s + 96, s + 96);
+          // S of block kb exists => its K / V have landed.  Once per stream and item (both streams write the same bytes;
+          // ordered before this stream's P.V of the block by the p_full arrival below), while the loads above are in flight:
+          //   * V rows past klen -> 0 (their P is 0, but 0 x stale inf / NaN bits would not be);
+          //   * V column dk of the valid rows -> 1.0: P.V multiplies all 64 columns of the tile anyway, so O[:, dk] becomes
+          //     the row sum of the fp16 P that the tensor core actually used -- the softmax denominator costs no
+          //     instruction here and follows every rescaling of O by construction
+          if (qt == wg) {
+            uint8_t* v_tile = sV + kb * kTileBytes;
+            if (r < nvalid) *reinterpret_cast<__half*>(v_tile + r * 128 + ((((p.dk >> 3)) ^ (r & 7)) << 4)) = __float2half_rn(1.0f);
+            zero_v_tail(v_tile, r, nvalid);
+          }
           ptx::tmem_ld_wait();
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&s_empty[wg]);   // the block is in registers: S(kb + 1) may overwrite it
-          // S of block kb exists => its K / V have landed: clear the V rows past klen once per stream and item (both
-          // streams write the same zeros); ordered before this stream's P.V of the block by the p_full arrival below
-          if (qt == wg && nvalid < 128) zero_v_tail(sV + kb * kTileBytes, r, nvalid);
           // ---- block maximum (keys past klen hold whatever the neighbouring rows produced: never looked at)
           float bm;
           if (nvalid == 128) {
@@ -317,12 +343,12 @@ __global__ void __launch_bounds__(kThreads, 1) attention_kernel(const __grid_con
             corr = ex2(mc - bml);
             mc = bml;
           }
-          // P.V of the previous block has retired: the P columns are free and O is current
+          // P.V of the previous block has retired: the P columns are free and O (with its row-sum column) is current
           ptx::mbar_wait(&p_empty[wg], (n_s & 1) ^ 1);
+          ptx::tc_fence_after();
           if (kb > 0 && __any_sync(0xffffffffu, move)) {
-            ptx::tc_fence_after();
-            sum *= corr;
-            for (int c = 0; c < p.dk; c += 16) {
+#pragma unroll 1
+            for (int c = 0; c < 64; c += 16) {
               uint32_t o[16];
               ptx::tmem_ld_32x32b_x16(t_s + kOCol + c, o);
               ptx::tmem_ld_wait();
@@ -332,17 +358,16 @@ __global__ void __launch_bounds__(kThreads, 1) attention_kernel(const __grid_con
             }
           }
           // ---- p = exp2(s * scale - reference) -> packed fp16, 32 keys (16 columns) per store
-          float sum1 = 0.f;
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             uint32_t pk[16];
             if ((c + 1) * 32 <= nvalid) {
 #pragma unroll
               for (int j = 0; j < 32; j += 2) {
-                const float p0 = ex2(fmaf(__uint_as_float(s[c * 32 + j]), p.scale_log2, -mc));
-                const float p1 = ex2(fmaf(__uint_as_float(s[c * 32 + j + 1]), p.scale_log2, -mc));
-                sum += p0;
-                sum1 += p1;
+                const float x0 = fmaf(__uint_as_float(s[c * 32 + j]), p.scale_log2, -mc);
+                const float x1 = fmaf(__uint_as_float(s[c * 32 + j + 1]), p.scale_log2, -mc);
+                const float p0 = ex2(x0);
+                const float p1 = ex2(x1);
                 __half2 hh = __floats2half2_rn(p0, p1);
                 pk[j >> 1] = *reinterpret_cast<uint32_t*>(&hh);
               }
@@ -351,15 +376,12 @@ __global__ void __launch_bounds__(kThreads, 1) attention_kernel(const __grid_con
               for (int j = 0; j < 32; j += 2) {
                 const float p0 = (c * 32 + j < nvalid) ? ex2(fmaf(__uint_as_float(s[c * 32 + j]), p.scale_log2, -mc)) : 0.f;
                 const float p1 = (c * 32 + j + 1 < nvalid) ? ex2(fmaf(__uint_as_float(s[c * 32 + j + 1]), p.scale_log2, -mc)) : 0.f;
-                sum += p0;
-                sum1 += p1;
                 __half2 hh = __floats2half2_rn(p0, p1);
                 pk[j >> 1] = *reinterpret_cast<uint32_t*>(&hh);
               }
             }
             ptx::tmem_st_32x32b_x16(t_s + kPCol + c * 16, pk);
           }
-          sum += sum1;
           ptx::tmem_st_wait();
           ptx::tc_fence_before();
           __syncwarp();
@@ -368,29 +390,49 @@ __global__ void __launch_bounds__(kThreads, 1) attention_kernel(const __grid_con
         // ---- O / sum -> fp16 (a row without a single valid key gets zeros)
         ptx::mbar_wait(&p_empty[wg], (n_s & 1) ^ 1);   // the last P.V of this query tile has retired
         ptx::tc_fence_after();
-        uint32_t ov[48];
+        uint32_t ov[64];
         ptx::tmem_ld_32x32b_x16(t_s + kOCol, ov);
         ptx::tmem_ld_32x32b_x16(t_s + kOCol + 16, ov + 16);
         ptx::tmem_ld_32x32b_x16(t_s + kOCol + 32, ov + 32);
+        ptx::tmem_ld_32x32b_x16(t_s + kOCol + 48, ov + 48);
         ptx::tmem_ld_wait();
+        const float sum = __uint_as_float(p.dk == 48 ? ov[48] : (p.dk == 32 ? ov[32] : ov[16]));   // column dk: the row sum of P
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&o_empty[wg]);
         const float inv = sum > 0.f ? 1.0f / sum : 0.f;
-        const int q = qt * 128 + r;
-        if (q < g.qlim) {
-          __half* dst = p.out + (static_cast<size_t>(g.row0) + q) * p.ld_out + h * p.dk;
+        uint32_t o16[24];   // this thread's output row, packed fp16
 #pragma unroll
-          for (int c = 0; c < 48; c += 8) {
-            if (c < p.dk) {
-              uint32_t o[4];
+        for (int j = 0; j < 48; j += 2) {
+          __half2 hh = __floats2half2_rn(__uint_as_float(ov[j]) * inv, __uint_as_float(ov[j + 1]) * inv);
+          o16[j >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+        }
+        const int nch = p.dk >> 3;   // 16-byte chunks per output row
+        if (p.stage) {
+          // A thread owns a ROW (96 bytes, 1 536 bytes from its neighbour's): stored directly, every instruction of the warp
+          // would touch 32 lines with 16 bytes each.  Through the warp's staging tile the same bytes leave as runs of whole
+          // rows: lane l of store i writes chunk (32 i + l) of the tile in row-major order.
+          __syncwarp();
 #pragma unroll
-              for (int j = 0; j < 8; j += 2) {
-                __half2 hh = __floats2half2_rn(__uint_as_float(ov[c + j]) * inv, __uint_as_float(ov[c + j + 1]) * inv);
-                o[j >> 1] = *reinterpret_cast<uint32_t*>(&hh);
-              }
-              *reinterpret_cast<uint4*>(dst + c) = make_uint4(o[0], o[1], o[2], o[3]);
-            }
+          for (int c = 0; c < 6; ++c)
+            if (c < nch)
+              *reinterpret_cast<uint4*>(stage_w + lane * kStagePitch + c * 16) = make_uint4(o16[4 * c], o16[4 * c + 1], o16[4 * c + 2], o16[4 * c + 3]);
+          __syncwarp();
+          const int q0 = qt * 128 + quad * 32;
+          __half* dst0 = p.out + (static_cast<size_t>(g.row0) + q0) * p.ld_out + h * p.dk;
+          for (int f = lane; f < 32 * nch; f += 32) {
+            const int row = f / nch, ch = f - row * nch;
+            if (q0 + row < g.qlim)
+              *reinterpret_cast<uint4*>(dst0 + static_cast<size_t>(row) * p.ld_out + ch * 8) =
+                  *reinterpret_cast<const uint4*>(stage_w + row * kStagePitch + ch * 16);
+          }
+        } else {
+          const int q = qt * 128 + r;
+          if (q < g.qlim) {
+            __half* dst = p.out + (static_cast<size_t>(g.row0) + q) * p.ld_out + h * p.dk;
+#pragma unroll
+            for (int c = 0; c < 6; ++c)
+              if (c < nch) *reinterpret_cast<uint4*>(dst + c * 8) = make_uint4(o16[4 * c], o16[4 * c + 1], o16[4 * c + 2], o16[4 * c + 3]);
           }
         }
       }
@@ -416,7 +458,10 @@ int launch_attention(const CUtensorMap* tmap_qkv, const int* klen, const int* cu
   p.nkb = nkb;
   p.B = B;
   p.H = H;
+  // shared memory: `ring` sets of K / V blocks + two Q tiles + barriers (+ the output staging tiles where they still fit:
+  // T' <= 256 and 384 < T' <= 640).  Measured on the c3 shape (T' = 376), a second K / V set is worth more than staging
   p.ring = nkb <= 3 ? 2 : 1;
+  p.stage = (p.ring * 2 * nkb + 2) * kTileBytes + kBarBytes + kStageBytes + 1024 <= 227 * 1024 ? 1 : 0;
   p.klen = klen;
   p.cu = cu;
   p.out = out;
@@ -427,7 +472,7 @@ int launch_attention(const CUtensorMap* tmap_qkv, const int* klen, const int* cu
   if (attr_once.first()) cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   const int items = B * H;
   const int grid = items < num_sms ? items : num_sms;
-  const int smem = (p.ring * 2 * nkb + 2) * kTileBytes + 512 + 1024;
+  const int smem = (p.ring * 2 * nkb + 2) * kTileBytes + kBarBytes + (p.stage ? kStageBytes : 0) + 1024;
   return launch_k(attention_kernel, dim3(grid), dim3(kThreads), smem, s, *tmap_qkv, p) == cudaSuccess ? 0 : -2;
 }
 

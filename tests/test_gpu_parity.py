@@ -89,6 +89,42 @@ def test_attention_matches_masked_softmax(eng_ctc, dev, B, T, lens):
     assert rel(out.float(), want) < 1e-3
 
 
+@pytest.mark.parametrize("B,T,lens", [(2, 251, [251, 140]), (2, 626, [626, 417]), (1, 128, None)])
+def test_attention_peaked_rows_move_the_softmax_reference(eng_ctc, dev, B, T, lens):
+    """The kernel exponentiates each 32-key chunk against a reference point that the first chunk of a query tile sets and
+    later chunks move only when they exceed it by more than 2^8 (attention_sm100.cu).  Score rows whose spread grows along
+    the key axis (key norms ramp up, queries are scaled) make the reference move many times per row -- across chunks of a
+    block and across blocks -- so the rescaling of the running sum, of the block's packed P and of O is exercised."""
+    g = torch.Generator().manual_seed(B * 77 + T)
+    d, H, dk = 768, 16, 48
+    x = torch.randn(B, T, 3, H, dk, generator=g)
+    x[:, :, 0] *= 6.0                                                      # queries: scores ~ N(0, 6^2 * |k|^2 / 48)
+    x[:, :, 1] *= (0.1 + 2.4 * torch.arange(T) / T)[None, :, None, None]   # key norms ramp up along the sequence
+    qkv = x.reshape(B * T, 3 * d).half().to(dev)
+    out = torch.zeros(B * T, d, dtype=torch.float16, device=dev)
+    klen = torch.tensor(lens, dtype=torch.int32, device=dev) if lens else None
+    rc = eng_ctc.lib.gam_test_attention(eng_ctc.handle, qkv.data_ptr(), klen.data_ptr() if lens else None, out.data_ptr(), B, T, _stream())
+    torch.cuda.synchronize()
+    assert rc == 0
+    xf = qkv.float().view(B, T, 3, H, dk)
+    q, k, v = (xf[:, :, i].transpose(1, 2) for i in range(3))
+    sc = q @ k.transpose(-1, -2) / dk ** 0.5
+    if lens:
+        valid = torch.arange(T, device=dev)[None, :] < klen[:, None]
+        sc = sc.masked_fill(~valid[:, None, None, :], float("-inf"))
+    # the test must do what it says: per row, count the chunks whose maximum beats everything before it by > 8 in log2 units
+    l2 = (sc * 1.4426950408889634).masked_fill(sc == float("-inf"), -1e30)
+    pad = (-T) % 32
+    cmax = F.pad(l2, (0, pad), value=-1e30).view(B, H, T, -1, 32).amax(-1)
+    run = torch.cummax(cmax, -1).values
+    moves = (cmax[..., 1:] > run[..., :-1] + 8.0).sum(-1).float().mean()
+    print(f"reference moves per row (upper bound of what the kernel sees): {float(moves):.2f}")
+    assert float(moves) > 1.0
+    want = (torch.softmax(sc, -1) @ v).transpose(1, 2).reshape(B * T, d)
+    assert torch.isfinite(out).all()
+    assert rel(out.float(), want) < 2e-3
+
+
 @pytest.mark.parametrize("B,sec,ragged", [(2, 2.0, True), (3, 10.0, False), (1, 0.5, False), (1, 0.2, False), (1, 0.3125, False)])
 def test_logmel_matches_oracle(eng_ctc, v2_ctc_ckpt, B, sec, ragged):
     wav, _ = synthetic.synthetic_audio(B, sec, seed=11, ragged=ragged)

@@ -4,7 +4,7 @@ mkdir -p gpurun_out
 P=gpurun_out/r2l
 timeout -k 5 200 python -m pytest tests/test_gpu_parity.py -q -m gpu -k "attention" 2>&1 | tail -25 > ${P}_attention.log
 tail -12 ${P}_attention.log
-timeout -k 5 600 python -m pytest tests/test_gpu_parity.py -q -m gpu -s -k "stagewise or golden or varlen or config2 or config5 or 25s or 30s or batch_vs_single or v1_batch" 2>&1 | tail -40 > ${P}_encoder.log
+timeout -k 5 600 python -m pytest tests/test_gpu_parity.py -q -m gpu -s -k "stagewise or varlen_ragged or config5 or 30s" 2>&1 | tail -40 > ${P}_encoder.log
 grep -v "^$" ${P}_encoder.log | tail -25
 timeout -k 5 300 python bench.py --gpus 1 --steps 20 --warmup 5 > ${P}_bench_n1.json 2> ${P}_bench_n1.err
 timeout -k 5 300 python tools/bench_configs.py c3 c5 > ${P}_configs.jsonl 2> ${P}_configs.err
@@ -21,3 +21,6 @@ for l in open('gpurun_out/r2l_configs.jsonl'):
         c=json.loads(l); print(c["config"], c["ms_per_batch"], c["utt_per_s"], c["classes_ms"])
     except Exception as e: print(l[:200])
 PY
+timeout -k 5 300 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:attention_kernel -c 1 \
+    -o gpurun_out/r2m_attn_c2 -f python tools/profile_step.py --layers 1 > gpurun_out/r2m_ncu_c2.log 2>&1
+tail -1 gpurun_out/r2m_ncu_c2.log
