@@ -29,15 +29,17 @@
 // other 15 are dropped).
 //
 // Persistent CTA per SM over (utterance, head) items; two query-tile streams per CTA (a softmax warpgroup + an MMA
-// issuer warp + 256 TMEM columns each: S [0,128) | P [128,192) | O [192,256)) take alternate query tiles of the item.
+// issuer warp + 256 TMEM columns each: S [0,128) | P [128,192) | O [192,256)) take alternate query tiles of the item;
+// a fourth warpgroup turns finished O tiles into output rows for both streams.
 // The item's K / V blocks are resident in shared memory and shared by both streams; with up to 3 key blocks (T' <= 384)
 // a second set of K / V buffers lets the producer fetch the next item while this one is computed.  Output rows leave
 // through a per-warp staging tile as runs of whole rows (see the epilogue).
 //
-// Measured (tools/attn_probe.py, profiles/r2n_attn_probe.txt): 55 us per launch at the c2 shape (64 x 251; the two-sweep
-// kernels it replaces: 56), 61 us at c3 (32 x 376; before: 89), 139 us at 32 x 626 (before: 191).  Moving a quarter or a half
-// of the exponentials to the FMA pipe (Cody-Waite + cubic) changed nothing: the softmax warps are bound by the latency of
-// their serial block chain (ld -> max -> exp -> st -> P.V -> O), not by MUFU or issue throughput.
+// Measured (tools/attn_probe.py, profiles/r2n_attn_probe.txt), one launch with a flushed L2: 47 us at the c2 shape
+// (64 x 251; the two-sweep kernels this replaces: 56), 55 us at c3 (32 x 376; before: 89), 131 us at 32 x 626 (before: 191).
+// Tried and dropped: walking a block in 32-score chunks with the next tcgen05.ld in flight (slower: per-chunk reference
+// logic), and moving a quarter / a half of the exponentials to the FMA pipe (Cody-Waite + cubic: no change) -- the softmax
+// warps are bound by the latency of their serial block chain (ld -> max -> exp -> st), not by MUFU or issue throughput.
 #include "kernels.h"
 #include "launch.cuh"
 #include "ptx.cuh"
@@ -47,12 +49,12 @@ namespace {
 
 constexpr int kMaxKB = 6;              // up to 768 keys (30 s segments of the reference's VAD, gigaam/vad_utils.py:85)
 constexpr int kTileBytes = 128 * 128;  // 128 rows x 64 fp16
-constexpr int kThreads = 384;          // warp 0 TMA, 1 / 2 MMA issuers, 3 TMEM owner, 4-7 / 8-11 softmax warpgroups
+constexpr int kThreads = 512;          // warp 0 TMA, 1 / 2 MMA issuers, 3 TMEM owner, 4-7 / 8-11 softmax warpgroups, 12-15 output
 constexpr uint32_t kPCol = 128, kOCol = 192;
 constexpr float kLazyLog2 = 8.0f;      // the softmax reference point trails the running maximum by at most 2^8
 constexpr int kBarBytes = 512;         // mbarriers + TMEM base slot
 constexpr int kStagePitch = 112;       // bytes per staged output row (96 used): conflict-free 16-byte accesses
-constexpr int kStageBytes = 8 * 32 * kStagePitch;   // one 32-row staging tile per softmax warp
+constexpr int kStageBytes = 4 * 32 * kStagePitch;   // one 32-row staging tile per output warp
 
 __device__ __forceinline__ float ex2(float x) {
   float y;
@@ -111,7 +113,8 @@ struct AttnParams {
 // mbar_wait(bar, j & 1), and waiting for completion j - 1 with j = 0 returns at once on a fresh barrier.
 //   per K / V set : kv_full[set][kb] (TMA bytes of K and V of block kb), kv_empty[set] (both streams are done with the item)
 //   per stream    : q_full / q_empty (Q tile), s_full (S block in TMEM) / s_empty (softmax has it in registers),
-//                   p_full (P block in TMEM) / p_empty (its P.V has retired: P free, O current), o_empty (O read out)
+//                   p_full (P block in TMEM) / p_empty (its P.V has retired: P free, O current),
+//                   o_full (last P.V of a query tile has retired) / o_empty (the output warpgroup has read O out)
 __global__ void __launch_bounds__(kThreads, 1) attention_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -128,7 +131,8 @@ __global__ void __launch_bounds__(kThreads, 1) attention_kernel(const __grid_con
   uint64_t* p_full = q_full + 8;
   uint64_t* p_empty = q_full + 10;
   uint64_t* o_empty = q_full + 12;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_full + 14);
+  uint64_t* o_full = q_full + 14;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_full + 16);
   uint8_t* sStage = reinterpret_cast<uint8_t*>(bars) + kBarBytes;
 
   const int warp_idx = threadIdx.x >> 5;
@@ -146,7 +150,8 @@ __global__ void __launch_bounds__(kThreads, 1) attention_kernel(const __grid_con
       ptx::mbar_init(&s_empty[i], 4);    // one arrival per softmax warp
       ptx::mbar_init(&p_full[i], 4);
       ptx::mbar_init(&p_empty[i], 1);
-      ptx::mbar_init(&o_empty[i], 4);
+      ptx::mbar_init(&o_empty[i], 4);    // one arrival per output warp
+      ptx::mbar_init(&o_full[i], 1);
     }
     ptx::fence_mbar_init();
   }
@@ -156,8 +161,9 @@ __global__ void __launch_bounds__(kThreads, 1) attention_kernel(const __grid_con
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // 384 threads x 168 registers fill the register file; a softmax thread holds a whole 128-score block, so warps 0-3
-  // (TMA / MMA issue / TMEM owner: a few dozen live values) hand their surplus to the two softmax warpgroups
+  // 512 threads x 128 registers fill the register file; a softmax thread holds a whole 128-score block, so warps 0-3
+  // (TMA / MMA issue / TMEM owner: a few dozen live values) and the output warpgroup hand their surplus to the two
+  // softmax warpgroups: 128 x 56 + 128 x 88 + 256 x 184 = 65 536
   // (each role's branch opens with its own setmaxnreg: ptxas budgets a branch by the instruction that dominates it)
   if (warp_idx == 0) {
     // ===================================================== TMA producer
@@ -203,77 +209,124 @@ __global__ void __launch_bounds__(kThreads, 1) attention_kernel(const __grid_con
     const int ksteps_qk = p.dk / 16;
     const uint32_t t_s = tmem_base + wg * 256;
     const uint32_t qa = ptx::smem_u32(sQ + wg * kTileBytes);
-    int it = 0;
-    uint32_t n_q = 0, n_s = 0, n_p = 0;   // Q tiles, S blocks and P.V products issued by this stream so far
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      const ItemGeom g = item_geom(p.klen, p.cu, item / p.H, p.T, nkb);
-      if (g.nq == 0) continue;
-      const int set = it % p.ring;
-      const uint32_t use = static_cast<uint32_t>(it / p.ring);
-      ++it;
-      uint8_t* sK = smem + set * set_bytes;
-      uint8_t* sV = sK + nkb * kTileBytes;
-      if (wg >= g.nq) {
-        // no query tile of this item for this stream: release the buffers, but only after the item's first load has
-        // completed, so that a stream can never arrive twice within one phase of kv_empty
-        ptx::mbar_wait(&kv_full[set * kMaxKB], use & 1);
-        if (ptx::elect_one()) ptx::mbar_arrive(&kv_empty[set]);
-        __syncwarp();
-        continue;
-      }
-      for (int qt = wg; qt < g.nq; qt += 2) {
-        const bool first_q = qt == wg, last_q = qt + 2 >= g.nq;
-        ptx::mbar_wait(&q_full[wg], n_q & 1);
-        for (int kb = 0; kb <= g.nk; ++kb) {
-          if (kb < g.nk) {
-            // S(kb): the softmax must have pulled the previous S block into registers
-            ptx::mbar_wait(&s_empty[wg], (n_s & 1) ^ 1);
-            if (first_q) ptx::mbar_wait(&kv_full[set * kMaxKB + kb], use & 1);
-            ptx::tc_fence_after();
-            if (ptx::elect_one()) {
-              const uint32_t ka = ptx::smem_u32(sK + kb * kTileBytes);
-              for (int k = 0; k < ksteps_qk; ++k)
-                ptx::mma_f16_ss(t_s, ptx::make_smem_desc_sw128(qa + k * 32, 16, 1024), ptx::make_smem_desc_sw128(ka + k * 32, 16, 1024),
-                                kIdescS, k != 0 ? 1u : 0u);
-              ptx::mma_commit(&s_full[wg]);
-              if (kb == g.nk - 1) ptx::mma_commit(&q_empty[wg]);   // last use of this Q tile
-            }
-            __syncwarp();
-            ++n_s;
-          }
-          if (kb > 0) {
-            // O (+)= P(kb-1) V(kb-1), issued behind S(kb) so that the tensor core is never waiting for a softmax
-            const int pb = kb - 1;
-            ptx::mbar_wait(&p_full[wg], n_p & 1);
-            if (pb == 0) ptx::mbar_wait(&o_empty[wg], (n_q & 1) ^ 1);   // the previous query tile's O has been read out
-            ptx::tc_fence_after();
-            if (ptx::elect_one()) {
-              const uint32_t va = ptx::smem_u32(sV + pb * kTileBytes);
-#pragma unroll
-              for (int ks = 0; ks < 8; ++ks)
-                ptx::mma_f16_ts(t_s + kOCol, t_s + kPCol + ks * 8, ptx::make_smem_desc_sw128(va + ks * 2048, 1024, 1024), kIdescPV,
-                                (pb | ks) != 0 ? 1u : 0u);
-              ptx::mma_commit(&p_empty[wg]);
-              if (pb == g.nk - 1 && last_q) ptx::mma_commit(&kv_empty[set]);   // this stream is done with the item
-            }
-            __syncwarp();
-            ++n_p;
-          }
+    uint32_t n_q = 0, n_s = 0, n_p = 0;   // query tiles completed, S blocks and P.V products issued by this stream so far
+
+    // ---- the stream's query tiles in order, across items (items without a tile for this stream are released on the way)
+    struct Tile {
+      int valid, nk, set, first_q, last_q;
+      uint32_t use;
+    };
+    int it = 0, item = blockIdx.x, qt_next = 0, cur_nq = 0, cur_nk = 0, cur_set = 0;
+    uint32_t cur_use = 0;
+    const int item_stride = gridDim.x;
+    // geometry of the next item not yet opened, fetched one item ahead (two dependent global loads off the issue path)
+    ItemGeom g_ahead = item_geom(p.klen, p.cu, min(item, n_items - 1) / p.H, p.T, nkb);
+    auto next_tile = [&]() -> Tile {
+      for (;;) {
+        if (qt_next < cur_nq) {
+          Tile t{1, cur_nk, cur_set, qt_next == wg, qt_next + 2 >= cur_nq, cur_use};
+          qt_next += 2;
+          return t;
         }
-        ++n_q;
+        if (item >= n_items) return Tile{0, 0, 0, 0, 0, 0u};
+        const ItemGeom g = g_ahead;
+        item += item_stride;
+        g_ahead = item_geom(p.klen, p.cu, min(item, n_items - 1) / p.H, p.T, nkb);
+        cur_nq = 0;
+        if (g.nq == 0) continue;
+        cur_set = it % p.ring;
+        cur_use = static_cast<uint32_t>(it / p.ring);
+        ++it;
+        if (wg >= g.nq) {
+          // no query tile of this item for this stream: release the buffers, but only after the item's first load has
+          // completed, so that a stream can never arrive twice within one phase of kv_empty
+          ptx::mbar_wait(&kv_full[cur_set * kMaxKB], cur_use & 1);
+          if (ptx::elect_one()) ptx::mbar_arrive(&kv_empty[cur_set]);
+          __syncwarp();
+          continue;
+        }
+        cur_nq = g.nq;
+        cur_nk = g.nk;
+        qt_next = wg;
       }
+    };
+    // S(kb) of tile t: the softmax must have pulled the previous S block into registers
+    auto issue_s = [&](const Tile& t, int kb) {
+      ptx::mbar_wait(&s_empty[wg], (n_s & 1) ^ 1);
+      if (t.first_q) ptx::mbar_wait(&kv_full[t.set * kMaxKB + kb], t.use & 1);
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
+        const uint32_t ka = ptx::smem_u32(smem + t.set * set_bytes + kb * kTileBytes);
+        for (int k = 0; k < ksteps_qk; ++k)
+          ptx::mma_f16_ss(t_s, ptx::make_smem_desc_sw128(qa + k * 32, 16, 1024), ptx::make_smem_desc_sw128(ka + k * 32, 16, 1024), kIdescS,
+                          k != 0 ? 1u : 0u);
+        ptx::mma_commit(&s_full[wg]);
+        if (kb == t.nk - 1) ptx::mma_commit(&q_empty[wg]);   // last use of this Q tile
+      }
+      __syncwarp();
+      ++n_s;
+    };
+    // O (+)= P(pb) V(pb) of tile t
+    auto issue_pv = [&](const Tile& t, int pb) {
+      ptx::mbar_wait(&p_full[wg], n_p & 1);
+      if (pb == 0) ptx::mbar_wait(&o_empty[wg], (n_q & 1) ^ 1);   // the previous query tile's O has been read out
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
+        const uint32_t va = ptx::smem_u32(smem + t.set * set_bytes + (nkb + pb) * kTileBytes);
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks)
+          ptx::mma_f16_ts(t_s + kOCol, t_s + kPCol + ks * 8, ptx::make_smem_desc_sw128(va + ks * 2048, 1024, 1024), kIdescPV,
+                          (pb | ks) != 0 ? 1u : 0u);
+        ptx::mma_commit(&p_empty[wg]);
+        if (pb == t.nk - 1) ptx::mma_commit(&o_full[wg]);                 // the query tile's O is complete
+        if (pb == t.nk - 1 && t.last_q) ptx::mma_commit(&kv_empty[t.set]);   // this stream is done with the item
+      }
+      __syncwarp();
+      ++n_p;
+    };
+
+    // Issue order per tile: S(0) | S(1) PV(0) | S(2) PV(1) | ... | S'(0) PV(nk-1): every P.V goes out behind the NEXT S, so
+    // the tensor core never waits for a softmax -- including across tiles: S'(0) of the stream's next tile is issued ahead of
+    // this tile's last P.V (its softmax then finds its scores waiting).  Looking ahead may cross into the NEXT item only,
+    // and only when that item has its own K / V buffers (ring == 2) and a tile for this stream: the loads of any item
+    // that reuses this item's buffers wait for this tile's last P.V, which would then wait for them.
+    Tile t = next_tile();
+    bool s0_issued = false;
+    while (t.valid) {
+      if (!s0_issued) {
+        ptx::mbar_wait(&q_full[wg], n_q & 1);
+        issue_s(t, 0);
+      }
+      for (int kb = 1; kb < t.nk; ++kb) {
+        issue_s(t, kb);
+        issue_pv(t, kb - 1);
+      }
+      Tile n{0, 0, 0, 0, 0, 0u};
+      const bool look = qt_next < cur_nq || (p.ring == 2 && item < n_items && g_ahead.nq > wg);
+      s0_issued = false;
+      if (look) {
+        n = next_tile();
+        if (n.valid) {
+          ptx::mbar_wait(&q_full[wg], (n_q + 1) & 1);
+          issue_s(n, 0);
+          s0_issued = true;
+        }
+      }
+      issue_pv(t, t.nk - 1);
+      ++n_q;
+      if (!look) n = next_tile();
+      t = n;
     }
   } else if (warp_idx == 3) {
     ptx::setmaxnreg_dec<56>();   // TMEM owner: idles until the teardown, but its warpgroup releases registers as one
-  } else {
+  } else if (warp_idx < 12) {
     // ===================================================== softmax warpgroup of stream wg (thread = query row)
-    ptx::setmaxnreg_inc<216>();
+    ptx::setmaxnreg_inc<184>();
     const int wg = (warp_idx - 4) >> 2;
     const int quad = warp_idx & 3;
     const int lane = threadIdx.x & 31;
     const int r = quad * 32 + lane;
     const uint32_t t_s = tmem_base + wg * 256 + (static_cast<uint32_t>(quad * 32) << 16);
-    uint8_t* stage_w = sStage + (warp_idx - 4) * (32 * kStagePitch);
     const int item_stride = gridDim.x;
     int it = 0;
     uint32_t n_s = 0;   // S blocks consumed by this stream so far
@@ -281,7 +334,6 @@ __global__ void __launch_bounds__(kThreads, 1) attention_kernel(const __grid_con
     int item = blockIdx.x;
     ItemGeom g_next = item_geom(p.klen, p.cu, min(item, n_items - 1) / p.H, p.T, nkb);
     for (; item < n_items; item += item_stride) {
-      const int h = item % p.H;
       const ItemGeom g = g_next;
       g_next = item_geom(p.klen, p.cu, min(item + item_stride, n_items - 1) / p.H, p.T, nkb);
       if (g.nq == 0) continue;
@@ -387,52 +439,75 @@ __global__ void __launch_bounds__(kThreads, 1) attention_kernel(const __grid_con
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&p_full[wg]);
         }
-        // ---- O / sum -> fp16 (a row without a single valid key gets zeros)
-        ptx::mbar_wait(&p_empty[wg], (n_s & 1) ^ 1);   // the last P.V of this query tile has retired
+        // (the query tile's output is the output warpgroup's business: this stream goes straight to its next tile)
+      }
+    }
+  } else {
+    // ===================================================== output warpgroup: O / row sum -> fp16 rows, for both streams.
+    // The denominator sits in column dk of O (see the softmax warps), so nothing is handed over in registers: the
+    // softmax warps never wait for the last P.V of a tile, the O read-out or the stores.
+    ptx::setmaxnreg_dec<88>();
+    const int quad = warp_idx & 3;
+    const int lane = threadIdx.x & 31;
+    uint8_t* stage_w = sStage + quad * (32 * kStagePitch);
+    const int nch = p.dk >> 3;   // 16-byte chunks per output row
+    const int item_stride = gridDim.x;
+    uint32_t n_o0 = 0, n_o1 = 0;   // query tiles read out per stream
+    int item = blockIdx.x;
+    ItemGeom g_next = item_geom(p.klen, p.cu, min(item, n_items - 1) / p.H, p.T, nkb);
+    for (; item < n_items; item += item_stride) {
+      const int h = item % p.H;
+      const ItemGeom g = g_next;
+      g_next = item_geom(p.klen, p.cu, min(item + item_stride, n_items - 1) / p.H, p.T, nkb);
+      for (int qt = 0; qt < g.nq; ++qt) {
+        const int wg = qt & 1;
+        const uint32_t t_o = tmem_base + wg * 256 + kOCol + (static_cast<uint32_t>(quad * 32) << 16);
+        ptx::mbar_wait(&o_full[wg], (wg ? n_o1 : n_o0) & 1);
+        if (wg) ++n_o1; else ++n_o0;
         ptx::tc_fence_after();
-        uint32_t ov[64];
-        ptx::tmem_ld_32x32b_x16(t_s + kOCol, ov);
-        ptx::tmem_ld_32x32b_x16(t_s + kOCol + 16, ov + 16);
-        ptx::tmem_ld_32x32b_x16(t_s + kOCol + 32, ov + 32);
-        ptx::tmem_ld_32x32b_x16(t_s + kOCol + 48, ov + 48);
+        uint32_t v[16];
+        ptx::tmem_ld_32x32b_x16(t_o + p.dk, v);   // column dk: the row sum of P (a row without a valid key: 0 -> zeros)
         ptx::tmem_ld_wait();
-        const float sum = __uint_as_float(p.dk == 48 ? ov[48] : (p.dk == 32 ? ov[32] : ov[16]));   // column dk: the row sum of P
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&o_empty[wg]);
+        const float sum = __uint_as_float(v[0]);
         const float inv = sum > 0.f ? 1.0f / sum : 0.f;
-        uint32_t o16[24];   // this thread's output row, packed fp16
+        const int q0 = qt * 128 + quad * 32;
+        __half* dst0 = p.out + (static_cast<size_t>(g.row0) + q0) * p.ld_out + h * p.dk;
+        if (p.stage) __syncwarp();   // the previous tile's copy out of the staging tile is complete
+        for (int c = 0; c < p.dk; c += 16) {
+          ptx::tmem_ld_32x32b_x16(t_o + c, v);
+          ptx::tmem_ld_wait();
+          if (c + 16 >= p.dk) {   // O is in registers: the stream's next tile may overwrite it
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&o_empty[wg]);
+          }
+          uint32_t o[8];
 #pragma unroll
-        for (int j = 0; j < 48; j += 2) {
-          __half2 hh = __floats2half2_rn(__uint_as_float(ov[j]) * inv, __uint_as_float(ov[j + 1]) * inv);
-          o16[j >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+          for (int j = 0; j < 16; j += 2) {
+            __half2 hh = __floats2half2_rn(__uint_as_float(v[j]) * inv, __uint_as_float(v[j + 1]) * inv);
+            o[j >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+          }
+          if (p.stage) {
+            uint4* d = reinterpret_cast<uint4*>(stage_w + lane * kStagePitch + c * 2);
+            d[0] = make_uint4(o[0], o[1], o[2], o[3]);
+            d[1] = make_uint4(o[4], o[5], o[6], o[7]);
+          } else if (q0 + lane < g.qlim) {
+            uint4* d = reinterpret_cast<uint4*>(dst0 + static_cast<size_t>(lane) * p.ld_out + c);
+            d[0] = make_uint4(o[0], o[1], o[2], o[3]);
+            d[1] = make_uint4(o[4], o[5], o[6], o[7]);
+          }
         }
-        const int nch = p.dk >> 3;   // 16-byte chunks per output row
         if (p.stage) {
           // A thread owns a ROW (96 bytes, 1 536 bytes from its neighbour's): stored directly, every instruction of the warp
-          // would touch 32 lines with 16 bytes each.  Through the warp's staging tile the same bytes leave as runs of whole
+          // touches 32 lines with 16 bytes each.  Through the warp's staging tile the same bytes leave as runs of whole
           // rows: lane l of store i writes chunk (32 i + l) of the tile in row-major order.
           __syncwarp();
-#pragma unroll
-          for (int c = 0; c < 6; ++c)
-            if (c < nch)
-              *reinterpret_cast<uint4*>(stage_w + lane * kStagePitch + c * 16) = make_uint4(o16[4 * c], o16[4 * c + 1], o16[4 * c + 2], o16[4 * c + 3]);
-          __syncwarp();
-          const int q0 = qt * 128 + quad * 32;
-          __half* dst0 = p.out + (static_cast<size_t>(g.row0) + q0) * p.ld_out + h * p.dk;
           for (int f = lane; f < 32 * nch; f += 32) {
-            const int row = f / nch, ch = f - row * nch;
+            const int row = nch == 6 ? f / 6 : f / nch;
+            const int ch = f - row * nch;
             if (q0 + row < g.qlim)
               *reinterpret_cast<uint4*>(dst0 + static_cast<size_t>(row) * p.ld_out + ch * 8) =
                   *reinterpret_cast<const uint4*>(stage_w + row * kStagePitch + ch * 16);
-          }
-        } else {
-          const int q = qt * 128 + r;
-          if (q < g.qlim) {
-            __half* dst = p.out + (static_cast<size_t>(g.row0) + q) * p.ld_out + h * p.dk;
-#pragma unroll
-            for (int c = 0; c < 6; ++c)
-              if (c < nch) *reinterpret_cast<uint4*>(dst + c * 8) = make_uint4(o16[4 * c], o16[4 * c + 1], o16[4 * c + 2], o16[4 * c + 3]);
           }
         }
       }
