@@ -19,6 +19,9 @@ CONFIGS = {
     "c5": ("v2_ssl", 128, 25.0),
     # not BASELINE configs: the rel_pos (v1) model on the c2 / c5 shapes
     "v1c2": ("v1_ctc", 64, 10.0), "v1c5": ("v1_ssl", 128, 25.0),
+    # not a BASELINE config either: the c2 batch with ragged lengths (uniform 1 .. 10 s inside the 10 s buffer) -- what varlen
+    # execution buys: only the frames that exist run through the encoder
+    "c2r": ("v2_ctc", 64, 10.0),
 }
 
 
@@ -28,6 +31,12 @@ def run(name):
     model = gigaam.load_model(model_name, device=dev, synthetic=True)
     eng = model._get_engine()
     wav, wav_len = gigaam.synthetic_audio(B, sec, seed=1234)
+    if name.endswith("r"):
+        g = torch.Generator().manual_seed(7)
+        wav_len = (torch.rand(B, generator=g) * 0.9 + 0.1).mul(sec * 16000).long()
+        wav_len[0] = int(sec * 16000)
+        wav = wav * (torch.arange(wav.shape[1])[None, :] < wav_len[:, None])
+    audio_fraction = float(wav_len.sum()) / float(B * wav.shape[1])
     wav, wav_len = wav.to(dev), wav_len.to(dev)
     has_head = hasattr(model, "head")
 
@@ -59,7 +68,8 @@ def run(name):
     step()
     prof = eng.profile_end()
     res = {"config": name, "model": model_name, "batch": B, "seconds": sec, "ms_per_batch": round(ms, 3),
-           "utt_per_s": round(B / ms * 1e3, 1), "rtfx": round(B * sec / ms * 1e3), "steps": n, "clocks": clocks,
+           "utt_per_s": round(B / ms * 1e3, 1), "rtfx": round(B * sec * audio_fraction / ms * 1e3), "audio_fraction": round(audio_fraction, 3),
+           "steps": n, "clocks": clocks,
            "classes_ms": {k: round(v[0], 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}}
     if has_head:
         counts = out[2]
