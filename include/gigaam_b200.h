@@ -150,7 +150,12 @@ int64_t gam_logmel_workspace_bytes(const gam_handle* h, int32_t B, int64_t n_sam
 int gam_logmel_tc(gam_handle* h, const float* wav, int32_t B, int64_t n_samples, float* mel, void* workspace,
                   int64_t workspace_bytes, void* stream);
 
-/* mel: device f32 [B, feat_in, M]; mel_len: device i64 [B]
+/* Varlen execution: lengths stay on the device (no host synchronisation, same launch sequence for every mix of lengths, so a
+ * captured CUDA graph of the call is valid for all of them).  From the second subsampling stage on only the frames that
+ * exist are computed (rows of the utterances packed back to back, cu_seqlens built by the first kernel of the call -- the
+ * contract of apply_masked_flash_attn, gigaam/utils.py:103-155, applied to the whole Conformer block); frames t >= enc_len[b]
+ * of `enc` are written as zeros.  A batch of ONE keeps its padded frames, like the reference (no attention mask for B == 1).
+ * mel: device f32 [B, feat_in, M]; mel_len: device i64 [B]
  * -> enc: device f32 [B, T', d_model] (row-major; the reference's [B, d, T'] is its transpose(1,2) view)
  *    enc_len: device i32 [B].  n_layers_run < 0 runs the full stack; 0..n_layers stops early (tests). */
 int gam_encode(gam_handle* h, const float* mel, const int64_t* mel_len, int32_t B, int64_t M, void* workspace,
