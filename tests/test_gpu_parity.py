@@ -869,11 +869,11 @@ def _pack(x_btc, lens):
     return torch.cat([x_btc[b, :n] for b, n in enumerate(lens)], 0)
 
 
-@pytest.mark.parametrize("relpos", [False, True])
 _MIXED_251 = [int(x) for x in np.random.default_rng(5).integers(0, 252, size=44)]    # 704 items: ~5 per persistent CTA,
 _MIXED_626 = [int(x) for x in np.random.default_rng(6).integers(0, 627, size=24)]    # 1-/2-tile and empty utterances interleaved
 
 
+@pytest.mark.parametrize("relpos", [False, True])
 @pytest.mark.parametrize("T,lens", [(251, [251, 97, 1, 0, 128, 129, 200]), (128, [5, 128, 64]), (751, [751, 129, 640, 300]),
                                     (376, [0, 376, 257, 31]), (251, _MIXED_251), (626, _MIXED_626)])
 def test_attention_varlen_packed_rows(request, dev, relpos, T, lens):
