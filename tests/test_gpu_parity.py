@@ -968,19 +968,20 @@ def test_varlen_rows_scale_with_audio_not_with_padding(dev, v2_ctc_ckpt):
     enc_f, _ = eng.encode(mel[:16].contiguous(), mel_len[:16])                    # the long ones alone
     assert rel(enc_r[:16], enc_f) < 1e-5 or float((enc_r[:16] - enc_f).abs().max()) < 1e-3
 
-    def timed(w, l):
+    def kernel_ms(w, l):
+        """Sum of the kernels' own durations (CUDA events around every launch, gam_profile_*): what the GPU spends on the
+        batch, free of the host's launch pace -- an eager step of 237 launches is launch-bound on a busy host."""
         w, l = w.to(dev), l.to(dev)
-        for _ in range(2):
+        model(w, l)
+        best = float("inf")
+        for _ in range(3):
+            eng.profile_begin()
             model(w, l)
-        torch.cuda.synchronize()
-        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0.record()
-        for _ in range(5):
-            model(w, l)
-        t1.record()
-        torch.cuda.synchronize()
-        return t0.elapsed_time(t1) / 5
-    t_full, t_rag = timed(wav, full_len), timed(wav_r, rag_len)
+            best = min(best, sum(ms for ms, _ in eng.profile_end().values()))
+        return best
+    t_full, t_rag = kernel_ms(wav, full_len), kernel_ms(wav_r, rag_len)
     frac = float(rag_len.sum()) / float(full_len.sum())
-    print(f"64 x 10 s: {t_full:.2f} ms; 16 x 10 s + 48 x 1 s in the same buffer ({frac:.2f} of the audio): {t_rag:.2f} ms")
-    assert t_rag < 0.6 * t_full
+    print(f"kernel time, 64 x 10 s: {t_full:.2f} ms; 16 x 10 s + 48 x 1 s in the same buffer ({frac:.2f} of the audio): {t_rag:.2f} ms")
+    # 0.33 of the audio; measured 0.51 of the kernel time: the front end and the CTC head run over the whole buffer, the short
+    # utterances still cost a 128 x 128 attention tile per head and a 256-row GEMM tile granularity, and kernels have floors
+    assert t_rag < 0.62 * t_full
