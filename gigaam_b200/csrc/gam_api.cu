@@ -447,6 +447,7 @@ int gam_encode(gam_handle* h, const float* mel, const int64_t* mel_len, int32_t 
                int64_t workspace_bytes, float* enc, int32_t* enc_len, int32_t n_layers_run, void* stream) {
   const gam_config& c = h->cfg;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (B <= 0 || M <= 0) return fail(h, -1, "encode: empty batch (B=%d, M=%lld); callers skip the call for an empty shard", B, (long long)M);
   Plan* p = get_plan(h, B, M, workspace, workspace_bytes);
   if (!p) return -1;
   if (p->T2 <= 0) return fail(h, -1, "input too short for the subsampling (M=%lld)", (long long)M);
