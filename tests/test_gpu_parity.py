@@ -538,7 +538,7 @@ def test_config4_per_gpu_size_against_oracle(dev, v3_ckpt):
 
 
 def test_config5_slice_against_oracle(dev):
-    """BASELINE.json configs[4]: v2_ssl embed path, 25 s utterances (T' = 626, the long attention kernel, s1 of
+    """BASELINE.json configs[4]: v2_ssl embed path, 25 s utterances (T' = 626: five key blocks, one K / V set per CTA in the attention kernel; s1 of
     0.5 G elements per 16 utterances); a 16-utterance slice of the 128 x 25 s batch."""
     ck = synthetic.synthetic_checkpoint("v2_ssl", seed=0)
     model = gigaam.load_model("v2_ssl", device=dev, checkpoint=ck)
