@@ -444,6 +444,38 @@ def main():
                     "step_frac": B * fl["total"] / (ms_per_step * 1e-3) / 1e12 / peak_tf,
                     "classes_ms_per_step": {k: round(v[0] / nprof, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}}
 
+    # ---- varlen leg (N = 1 only, outside the timed region): the same 64-utterance buffer with ragged lengths (uniform in
+    # 0.1 .. 1.0 of the 10 s).  Reported as summed kernel time (CUDA events around every launch) next to the full-length
+    # step's, because an eager step is paced by the host.  Never fatal: the contract line does not depend on it.
+    varlen = None
+    if rank == 0 and world == 1 and roofline is not None:
+        try:
+            gen = torch.Generator().manual_seed(7)
+            rag_len = (torch.rand(B, generator=gen) * 0.9 + 0.1).mul(n_samples).long()
+            rag_len[0] = n_samples
+            rag_len_dev = rag_len.to(dev)
+            rag_wav = wavs[0] * (torch.arange(n_samples, device=dev)[None, :] < rag_len_dev[:, None])
+            rag_mel_len = model.preprocessor.out_len(rag_len_dev)
+
+            def ragged_step():
+                enc, enc_len = eng.encode(eng.logmel(rag_wav), rag_mel_len)
+                return eng.greedy(enc, enc_len, packed)
+            ragged_step()
+            best = float("inf")
+            for _ in range(3):
+                eng.profile_begin()
+                ragged_step()
+                best = min(best, sum(ms for ms, _ in eng.profile_end().values()))
+            full_ms = sum(v[0] for v in prof.values()) / nprof
+            frac = float(rag_len.sum()) / float(B * n_samples)
+            varlen = {"workload": f"the same {B} x {SECONDS:g} s buffer, utterance lengths uniform in 0.1 .. 1.0 of it",
+                      "audio_fraction": round(frac, 3), "kernel_ms_full_lengths": round(full_ms, 3), "kernel_ms_ragged": round(best, 3),
+                      "utt_per_s_of_kernel_time": round(B / best * 1e3, 1),
+                      "note": "packed rows (cu_seqlens built on the device): only the frames that exist run through the encoder"}
+            del rag_wav
+        except Exception as e:  # noqa: BLE001
+            varlen = {"error": repr(e)[:300]}
+
     del pipe, graph
     strong = None if args.no_c4 else c4_strong_scaling(dev, rank, world)
     if rank == 0:
@@ -459,7 +491,7 @@ def main():
                                "hypotheses out, copies of neighbouring steps overlapped with compute, kernels replayed as one CUDA graph per shape",
                         "serial_value": e2e_serial_value},
                 "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
-                "roofline": roofline, "strong_scaling_c4": strong,
+                "roofline": roofline, "varlen": varlen, "strong_scaling_c4": strong,
                 "cpu_baseline": ({k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")} if cpu else None)}
         real_stdout.write(json.dumps(line) + "\n")
         real_stdout.flush()
