@@ -475,6 +475,10 @@ def main():
             del rag_wav
         except Exception as e:  # noqa: BLE001
             varlen = {"error": repr(e)[:300]}
+            try:
+                eng.profile_end()      # never leave the per-launch event profiler armed
+            except Exception:  # noqa: BLE001
+                pass
 
     del pipe, graph
     strong = None if args.no_c4 else c4_strong_scaling(dev, rank, world)
