@@ -136,3 +136,44 @@ def test_compiled_reference_archive_reproduces_the_golden_vectors(golden_dir, v2
     env = dict(**__import__("os").environ, GIGAAM_REFERENCE_ARCHIVE_ONLY="1")
     res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
     assert res.returncode == 0 and "archive ok" in res.stdout, res.stderr[-2000:]
+
+
+@pytest.mark.parametrize("which", ["v2_ctc", "v3_e2e_rnnt", "v1_ctc"])
+def test_oracle_matches_the_reference_on_a_strongly_ragged_batch(which):
+    """The varlen GPU tests (tests/test_gpu_parity.py::test_varlen_ragged_batch_against_oracle) compare packed-row execution with
+    the ORACLE on batches that run from a full buffer down to a two-frame utterance; the committed goldens only reach 0.5 of the
+    buffer.  This pins the oracle's masking / length arithmetic on such a batch to the reference itself (the byte-compiled
+    archive, imported on its own): log-mel, encoded lengths and the encoder output on every valid frame, for the three encoder
+    shapes (conv2d + BatchNorm + rotary, conv1d + LayerNorm, rel_pos), three layers deep."""
+    from oracle import ref_loader
+    if not ref_loader.ARCHIVE.is_file():
+        pytest.skip("oracle/_ref/gigaam_ref.zip not built (oracle/build_ref.py needs /root/reference)")
+    import subprocess
+    import sys
+    code = (
+        "import sys, torch\n"
+        f"sys.path.insert(0, {str(ref_loader.ROOT)!r})\n"
+        "from oracle.ref_loader import build_reference, reference_root\n"
+        "from oracle import gigaam_oracle as orc\n"
+        "from gigaam_b200 import synthetic\n"
+        "assert reference_root().endswith('gigaam_ref.zip')\n"
+        f"ck = synthetic.synthetic_checkpoint({which!r}, seed=0, n_layers=3)\n"
+        "root, dec = build_reference(ck['cfg'], ck['state_dict'])\n"
+        "secs = [4.0, 0.06, 1.3, 3.1, 0.5, 4.0]\n"
+        "wav, _ = synthetic.synthetic_audio(len(secs), 4.0, seed=4321)\n"
+        "wl = torch.tensor([int(s * 16000) for s in secs])\n"
+        "for b, n in enumerate(wl.tolist()): wav[b, n:] = 0.0\n"
+        "with torch.inference_mode():\n"
+        "    mel, ml = root.preprocessor(wav, wl); enc, el = root.encoder(mel, ml)\n"
+        "    enc_o, el_o = orc.model_forward(wav, wl, ck['state_dict'], ck['cfg'])\n"
+        "assert torch.equal(el.long(), el_o.long()), (el, el_o)\n"
+        "assert int(el.min()) <= 2 and int(el.max()) >= 100\n"
+        "valid = torch.arange(enc.shape[2])[None, :] < el[:, None]\n"
+        "a, b = enc_o.transpose(1, 2)[valid], enc.transpose(1, 2)[valid]\n"
+        "rel = float((a - b).norm() / b.norm())\n"
+        "worst = max(float((enc_o[i, :, :int(el[i])] - enc[i, :, :int(el[i])]).norm() / enc[i, :, :int(el[i])].norm()) for i in range(len(secs)))\n"
+        "assert rel < 1e-5 and worst < 1e-4, (rel, worst)\n"
+        "print('ragged ok', rel, worst)\n")
+    env = dict(**__import__("os").environ, GIGAAM_REFERENCE_ARCHIVE_ONLY="1")
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=900)
+    assert res.returncode == 0 and "ragged ok" in res.stdout, (res.stdout[-500:], res.stderr[-2000:])
